@@ -1,0 +1,218 @@
+/* jetb200.h — C ABI of the B200-native contraction engine behind the Jet API.
+ *
+ * This is the drop-in boundary for ONE path of XanaduAI/jet: pairwise tensor contraction
+ * (index permutation + complex GEMM) driven per slice over a sliced tensor network.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *   - All functions return 0 on success, non-zero on failure; jb_last_error() returns the message
+ *     of the calling thread's last failure (the C++ layer rethrows it as Jet::Exception, mirroring
+ *     include/jet/Abort.hpp:51-97).
+ *   - dtype: JB_C64 = std::complex<float>, JB_C128 = std::complex<double> (the only two element
+ *     types the reference supports, include/jet/Tensor.hpp:32-34).
+ *   - Tensors are dense, row-major over their extents (last axis fastest), like Jet::Tensor
+ *     (include/jet/Tensor.hpp:766-775).
+ *   - Pointers named d_* are DEVICE pointers, h_* are HOST pointers.  Kernels never allocate: all
+ *     buffers, including workspaces, are supplied by the caller (or owned by a jb_plan).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - All entry points are re-entrant; there is no hidden global stream or handle.
+ *   - There is NO CPU fallback: every call fails loudly if no CUDA device is usable.
+ */
+#ifndef JETB200_H
+#define JETB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_C64 0
+#define JB_C128 1
+#define JB_MAX_RANK 64
+
+/* ---- status / device --------------------------------------------------------------------- */
+const char *jb_last_error(void);
+const char *jb_version(void);
+int jb_device_count(int *count);
+int jb_set_device(int device);
+int jb_device_info(int device, int *sm_count, size_t *total_bytes, size_t *l2_bytes, int *cc_major,
+                   int *cc_minor);
+
+/* ---- device memory + streams (what cudaMalloc/cudaMemcpy are to include/jet/CudaTensor.hpp:158,
+ *      185,307; here explicit, asynchronous on a stream, and never called inside an operator) --- */
+int jb_malloc(void **d_ptr, size_t bytes);
+int jb_free(void *d_ptr);
+int jb_host_alloc(void **h_ptr, size_t bytes); /* pinned */
+int jb_host_free(void *h_ptr);
+int jb_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int jb_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int jb_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
+int jb_memset_zero(void *d_dst, size_t bytes, void *stream);
+int jb_stream_create(void **stream);
+int jb_stream_destroy(void *stream);
+int jb_stream_sync(void *stream);
+
+/* ---- K1: index permutation ----------------------------------------------------------------
+ * Replaces Permuter<Backend>::Transpose(data_in, shape, data_out, current_order, new_order)
+ * (include/jet/permute/Permuter.hpp:50-79; back ends permute/QFlex.hpp:37-50 and
+ * permute/Default.hpp:21-133), as called from Tensor::Transpose (include/jet/Tensor.hpp:594-611).
+ * extent_in[i] is the extent of input axis i; output axis j is input axis perm[j].
+ * Bit-exact (pure data movement).  in and out must not overlap. */
+int jb_permute(int dtype, const void *d_in, void *d_out, int rank, const int64_t *extent_in,
+               const int32_t *perm, void *stream);
+
+/* ---- K2: row-major complex GEMM  C(MxN) = A(MxK) * B(KxN), alpha = 1, beta = 0 ---------------
+ * Replaces gemmBinding / gemvBinding / dotuBinding -> cblas_{c,z}gemm / gemv / dotu_sub
+ * (include/jet/TensorHelpers.hpp:49-61,79-89,103-111) as dispatched by MultiplyTensorData
+ * (include/jet/TensorHelpers.hpp:131-168): lda = K, ldb = ldc = N; M == 1 and/or N == 1 are the
+ * GEMV / DOTU (unconjugated) corners.  jb_gemm_ws_bytes gives the split-K workspace size
+ * (may be 0); d_ws may be NULL when it is 0. */
+size_t jb_gemm_ws_bytes(int dtype, int64_t m, int64_t n, int64_t k);
+int jb_gemm(int dtype, int64_t m, int64_t n, int64_t k, const void *d_a, const void *d_b,
+            void *d_c, void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- fused pairwise contraction ---------------------------------------------------------------
+ * Replaces Tensor::ContractTensors(A, B) (include/jet/Tensor.hpp:709-752): modes are integer
+ * labels; equal labels are summed over (no conjugation).  The output is ordered
+ * (modes of A not in B, in A's order) ++ (modes of B not in A, in B's order) exactly as
+ * Tensor.hpp:732-741.  jb_contract_info reports the output rank/modes/extents, the GEMM view
+ * (M, N, K), the workspace the chosen kernel needs and which kernel family was chosen
+ * (0 = streaming FMA kernel with the small operand resident in shared memory,
+ *  1 = permute + GEMM through the workspace). */
+typedef struct jb_contract_info_t {
+    int32_t rank_c;
+    int32_t modes_c[JB_MAX_RANK];
+    int64_t extent_c[JB_MAX_RANK];
+    int64_t m, n, k;
+    size_t ws_bytes;
+    int32_t kernel;
+} jb_contract_info_t;
+
+int jb_contract_info(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
+                     int rank_b, const int64_t *extent_b, const int32_t *modes_b,
+                     jb_contract_info_t *info);
+int jb_contract(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
+                const void *d_a, int rank_b, const int64_t *extent_b, const int32_t *modes_b,
+                const void *d_b, void *d_c, void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- elementwise helpers --------------------------------------------------------------------
+ * jb_add: c = a + b elementwise over n complex elements; the aligned-add at the core of
+ * Tensor::AddTensors (include/jet/Tensor.hpp:433-451) — permute b first with jb_permute when its
+ * index order differs.  jb_slice: fixes axis `axis` of `in` to `value` and writes the rank-1
+ * smaller tensor, Tensor::SliceIndex (include/jet/Tensor.hpp:494-526).  jb_conj: elementwise
+ * conjugate (Tensor::Conj, include/jet/Tensor.hpp:668-675). */
+int jb_add(int dtype, int64_t n, const void *d_a, const void *d_b, void *d_c, void *stream);
+int jb_slice(int dtype, const void *d_in, void *d_out, int rank, const int64_t *extent_in,
+             int axis, int64_t value, void *stream);
+int jb_conj(int dtype, int64_t n, const void *d_in, void *d_out, void *stream);
+
+/* ---- host-buffer forms (what a Jet::Tensor method calls: host std::vector in, host std::vector
+ *      out; H2D copy, kernel(s), D2H copy and a stream sync happen inside) ---------------------- */
+int jb_permute_host(int dtype, const void *h_in, void *h_out, int rank, const int64_t *extent_in,
+                    const int32_t *perm);
+int jb_contract_host(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
+                     const void *h_a, int rank_b, const int64_t *extent_b, const int32_t *modes_b,
+                     const void *h_b, void *h_c);
+int jb_gemm_host(int dtype, int64_t m, int64_t n, int64_t k, const void *h_a, const void *h_b,
+                 void *h_c);
+int jb_add_host(int dtype, int64_t n, const void *h_a, const void *h_b, void *h_c);
+int jb_slice_host(int dtype, const void *h_in, void *h_out, int rank, const int64_t *extent_in,
+                  int axis, int64_t value);
+
+/* ---- contraction plan: a whole (sliced) network + path on one GPU ----------------------------
+ * Replaces the per-task execution of TaskBasedContractor (AddContractionTasks / AddReductionTask /
+ * AddDeletionTasks / Contract, include/jet/TaskBasedContractor.hpp:162-322) and the per-slice
+ * network copies made by TensorNetwork::SliceIndices (include/jet/TensorNetwork.hpp:210-284):
+ * the leaves live once in a device arena, slices are views selected on the device, every path
+ * step is a CUDA-graph kernel node, intermediates get arena offsets from their lifetimes, and the
+ * per-slice results are accumulated on the device in double precision.
+ *
+ * Network description: leaf i has rank[i] axes with extents extent[off_i..] and integer mode
+ * labels mode[off_i..] (off_i = sum of earlier ranks), data h_data[i] (host, row-major, dtype).
+ * path is num_steps pairs (a, b) of node ids; step s creates node num_leaves + s
+ * (include/jet/TensorNetwork.hpp:301-328).  sliced_modes lists the modes fixed per slice; a slice
+ * id is the row-major ravel over them, first listed mode slowest (TensorNetwork.hpp:210-230).
+ */
+typedef struct jb_plan jb_plan;
+
+typedef struct jb_network_desc_t {
+    int32_t dtype;
+    int32_t device;
+    int32_t num_leaves;
+    const int32_t *rank;   /* [num_leaves] */
+    const int64_t *extent; /* [sum rank] */
+    const int32_t *mode;   /* [sum rank] */
+    const void *const *h_data; /* [num_leaves] */
+    int32_t num_steps;
+    const int32_t *path; /* [2 * num_steps] */
+    int32_t num_sliced;
+    const int32_t *sliced_modes; /* [num_sliced] */
+    int32_t flags;               /* JB_PLAN_* */
+} jb_network_desc_t;
+
+#define JB_PLAN_KEEP_INTERMEDIATES 1 /* no buffer reuse: every step output stays readable */
+#define JB_PLAN_NO_GRAPH 2           /* launch kernels directly instead of through a CUDA graph */
+#define JB_PLAN_STORE_RESULTS 4      /* keep every slice's own result (for GetResults()) */
+
+typedef struct jb_plan_stats_t {
+    int64_t num_slices;        /* product of sliced extents */
+    int64_t result_elems;      /* elements of the final tensor */
+    int32_t result_rank;
+    int32_t result_modes[JB_MAX_RANK];
+    int64_t result_extent[JB_MAX_RANK];
+    int32_t steps_total;       /* path steps */
+    int32_t steps_shared;      /* slice-independent steps (run once, not per slice) */
+    int32_t steps_stream;      /* per-slice steps on the streaming kernel */
+    int32_t steps_ttgt;        /* per-slice steps on permute + GEMM */
+    int32_t launches_per_slice; /* kernel launches in one slice's graph */
+    double flops_per_slice;    /* 8*M*N*K summed over per-slice steps */
+    double bytes_per_slice;    /* sizeof(T)*(MK+KN+MN) summed over per-slice steps */
+    double flops_shared, bytes_shared;
+    double jet_flops_per_slice; /* 2*M*N*K over ALL steps: PathInfo::GetTotalFlops convention */
+    size_t arena_bytes;        /* device memory reserved */
+    int64_t max_step_elems;    /* largest intermediate */
+} jb_plan_stats_t;
+
+int jb_plan_create(const jb_network_desc_t *desc, jb_plan **plan);
+int jb_plan_destroy(jb_plan *plan);
+int jb_plan_stats(const jb_plan *plan, jb_plan_stats_t *stats);
+/* Upload leaf data again (H2D) — the host->device leg of an end-to-end run. */
+int jb_plan_upload(jb_plan *plan, const void *const *h_data);
+/* Zero the accumulator, (re)run the shared steps if needed. */
+int jb_plan_reset(jb_plan *plan);
+/* Enqueue `count` slices: ids first, first+1, ... (asynchronous; no host sync). */
+int jb_plan_run(jb_plan *plan, int64_t first_slice, int64_t count);
+/* Enqueue an explicit list of slice ids. */
+int jb_plan_run_list(jb_plan *plan, const int64_t *slice_ids, int64_t count);
+/* Wait, then read the double-precision sum over all slices run since the last reset:
+ * h_out receives result_elems (re, im) pairs of doubles. */
+int jb_plan_result(jb_plan *plan, double *h_out);
+/* With JB_PLAN_STORE_RESULTS: result of the ordinal-th slice run since reset, in dtype. */
+int jb_plan_slice_result(jb_plan *plan, int64_t ordinal, void *h_out);
+/* With JB_PLAN_KEEP_INTERMEDIATES: copy node `node`'s tensor (last slice run) to the host. */
+int jb_plan_node(jb_plan *plan, int32_t node, void *h_out, int64_t *elems);
+int jb_plan_sync(jb_plan *plan);
+/* Device time (ms) between the first and last kernel of the most recent jb_plan_run*, measured
+ * with CUDA events on the plan's stream. */
+int jb_plan_last_ms(jb_plan *plan, float *ms);
+/* The stream the plan launches on (cudaStream_t). */
+int jb_plan_stream(jb_plan *plan, void **stream);
+/* Per-step description for roofline accounting: fills up to cap entries. */
+typedef struct jb_step_info_t {
+    int32_t node_a, node_b, node_c;
+    int32_t shared;  /* 1 = slice-independent */
+    int32_t kernel;  /* 0 stream, 1 ttgt */
+    int64_t m, n, k;
+    double flops, bytes;
+} jb_step_info_t;
+int jb_plan_steps(const jb_plan *plan, jb_step_info_t *steps, int32_t cap, int32_t *count);
+/* Time every per-slice step individually (CUDA events, `reps` repetitions on the given slice);
+ * ms[i] is the mean device time of step i (0 for shared steps). */
+int jb_plan_profile(jb_plan *plan, int64_t slice, int reps, float *ms, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JETB200_H */

@@ -1,0 +1,175 @@
+"""ctypes binding of libjetb200.so (the C ABI in include/jetb200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable, the calls
+raise.  Build the library with ``python -c 'import __graft_entry__ as g; g.build()'`` or
+``make -C jet_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libjetb200.so")
+
+JB_C64, JB_C128 = 0, 1
+JB_MAX_RANK = 64
+JB_PLAN_KEEP_INTERMEDIATES = 1
+JB_PLAN_NO_GRAPH = 2
+JB_PLAN_STORE_RESULTS = 4
+
+
+class JetB200Error(RuntimeError):
+    """Raised for every non-zero status of the C ABI (message from jb_last_error())."""
+
+
+class ContractInfo(C.Structure):
+    _fields_ = [
+        ("rank_c", C.c_int32),
+        ("modes_c", C.c_int32 * JB_MAX_RANK),
+        ("extent_c", C.c_int64 * JB_MAX_RANK),
+        ("m", C.c_int64),
+        ("n", C.c_int64),
+        ("k", C.c_int64),
+        ("ws_bytes", C.c_size_t),
+        ("kernel", C.c_int32),
+    ]
+
+
+class NetworkDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("device", C.c_int32),
+        ("num_leaves", C.c_int32),
+        ("rank", C.POINTER(C.c_int32)),
+        ("extent", C.POINTER(C.c_int64)),
+        ("mode", C.POINTER(C.c_int32)),
+        ("h_data", C.POINTER(C.c_void_p)),
+        ("num_steps", C.c_int32),
+        ("path", C.POINTER(C.c_int32)),
+        ("num_sliced", C.c_int32),
+        ("sliced_modes", C.POINTER(C.c_int32)),
+        ("flags", C.c_int32),
+    ]
+
+
+class PlanStats(C.Structure):
+    _fields_ = [
+        ("num_slices", C.c_int64),
+        ("result_elems", C.c_int64),
+        ("result_rank", C.c_int32),
+        ("result_modes", C.c_int32 * JB_MAX_RANK),
+        ("result_extent", C.c_int64 * JB_MAX_RANK),
+        ("steps_total", C.c_int32),
+        ("steps_shared", C.c_int32),
+        ("steps_stream", C.c_int32),
+        ("steps_ttgt", C.c_int32),
+        ("launches_per_slice", C.c_int32),
+        ("flops_per_slice", C.c_double),
+        ("bytes_per_slice", C.c_double),
+        ("flops_shared", C.c_double),
+        ("bytes_shared", C.c_double),
+        ("jet_flops_per_slice", C.c_double),
+        ("arena_bytes", C.c_size_t),
+        ("max_step_elems", C.c_int64),
+    ]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [
+        ("node_a", C.c_int32),
+        ("node_b", C.c_int32),
+        ("node_c", C.c_int32),
+        ("shared", C.c_int32),
+        ("kernel", C.c_int32),
+        ("m", C.c_int64),
+        ("n", C.c_int64),
+        ("k", C.c_int64),
+        ("flops", C.c_double),
+        ("bytes", C.c_double),
+    ]
+
+
+# every symbol include/jetb200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "jb_last_error", "jb_version", "jb_device_count", "jb_set_device", "jb_device_info",
+    "jb_malloc", "jb_free", "jb_host_alloc", "jb_host_free", "jb_memcpy_h2d", "jb_memcpy_d2h",
+    "jb_memcpy_d2d", "jb_memset_zero", "jb_stream_create", "jb_stream_destroy", "jb_stream_sync",
+    "jb_permute", "jb_gemm_ws_bytes", "jb_gemm", "jb_contract_info", "jb_contract", "jb_add",
+    "jb_slice", "jb_conj", "jb_permute_host", "jb_contract_host", "jb_gemm_host", "jb_add_host",
+    "jb_slice_host", "jb_plan_create", "jb_plan_destroy", "jb_plan_stats", "jb_plan_upload",
+    "jb_plan_reset", "jb_plan_run", "jb_plan_run_list", "jb_plan_result", "jb_plan_slice_result",
+    "jb_plan_node", "jb_plan_sync", "jb_plan_last_ms", "jb_plan_stream", "jb_plan_steps",
+    "jb_plan_profile",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libjetb200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JetB200Error(
+                f"{LIB_PATH} is missing: build it with `make -C jet_b200/csrc` "
+                "(there is no CPU fallback)"
+            )
+        L = C.CDLL(LIB_PATH)
+        L.jb_last_error.restype = C.c_char_p
+        L.jb_version.restype = C.c_char_p
+        L.jb_gemm_ws_bytes.restype = C.c_size_t
+        L.jb_gemm_ws_bytes.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64]
+        L.jb_gemm.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jb_gemm_host.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]
+        L.jb_permute.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
+        L.jb_permute_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.jb_contract.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]
+        L.jb_contract_host.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.jb_contract_info.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.POINTER(ContractInfo)]
+        L.jb_add.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.jb_add_host.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.jb_conj.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.jb_slice.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                               C.c_int64, C.c_void_p]
+        L.jb_slice_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_int64]
+        L.jb_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.jb_free.argtypes = [C.c_void_p]
+        L.jb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.jb_host_free.argtypes = [C.c_void_p]
+        for name in ("jb_memcpy_h2d", "jb_memcpy_d2h", "jb_memcpy_d2d"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jb_memset_zero.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jb_stream_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.jb_stream_destroy.argtypes = [C.c_void_p]
+        L.jb_stream_sync.argtypes = [C.c_void_p]
+        L.jb_plan_create.argtypes = [C.POINTER(NetworkDesc), C.POINTER(C.c_void_p)]
+        L.jb_plan_destroy.argtypes = [C.c_void_p]
+        L.jb_plan_stats.argtypes = [C.c_void_p, C.POINTER(PlanStats)]
+        L.jb_plan_upload.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.jb_plan_reset.argtypes = [C.c_void_p]
+        L.jb_plan_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.jb_plan_run_list.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.jb_plan_result.argtypes = [C.c_void_p, C.c_void_p]
+        L.jb_plan_slice_result.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.jb_plan_node.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]
+        L.jb_plan_sync.argtypes = [C.c_void_p]
+        L.jb_plan_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.jb_plan_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.jb_plan_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.jb_plan_profile.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int32]
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise JetB200Error(lib().jb_last_error().decode(errors="replace"))

@@ -1,0 +1,108 @@
+// Shared declarations for the jetb200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "jetb200.h"
+
+namespace jb {
+
+// ---- error plumbing: every C entry point returns int and leaves a thread-local message --------
+std::string &LastError();
+int Fail(const std::string &msg);
+
+#define JB_CUDA(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t jb_err__ = (expr);                                                            \
+        if (jb_err__ != cudaSuccess) {                                                            \
+            return ::jb::Fail(std::string(#expr) + ": " + cudaGetErrorString(jb_err__));          \
+        }                                                                                         \
+    } while (0)
+
+#define JB_TRY(expr)                                                                              \
+    do {                                                                                          \
+        int jb_rc__ = (expr);                                                                     \
+        if (jb_rc__ != 0)                                                                         \
+            return jb_rc__;                                                                       \
+    } while (0)
+
+#define JB_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                          \
+        if (!(cond))                                                                              \
+            return ::jb::Fail(msg);                                                               \
+    } while (0)
+
+inline size_t ElemBytes(int dtype) { return dtype == JB_C64 ? 8 : 16; }
+inline bool IsPow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+inline int Log2(int64_t x)
+{
+    int l = 0;
+    while ((int64_t(1) << l) < x)
+        l++;
+    return l;
+}
+
+int NumSMs();
+
+// ---- K1: permutation ---------------------------------------------------------------------------
+// Bit-permutation description: the tensor has n address bits (all extents powers of two);
+// output address bit j is input address bit src[j].
+struct BitPerm {
+    int n = 0;
+    uint8_t src[64];
+};
+
+int LaunchPermute(int dtype, const void *in, void *out, int rank, const int64_t *extent,
+                  const int32_t *perm, cudaStream_t stream);
+
+// ---- K2: dense row-major GEMM -------------------------------------------------------------------
+size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k);
+int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c,
+               void *ws, size_t ws_bytes, cudaStream_t stream);
+
+// ---- fused contraction --------------------------------------------------------------------------
+// A prepared pairwise contraction: everything derived from shapes/modes on the host once, so that
+// launching it (many times, from a CUDA graph capture) is a pure kernel launch.
+struct StreamParams; // defined in contract.cu
+
+struct ContractPlan {
+    int dtype = JB_C64;
+    int rank_a = 0, rank_b = 0, rank_c = 0;
+    std::vector<int64_t> extent_a, extent_b, extent_c;
+    std::vector<int32_t> modes_a, modes_b, modes_c;
+    int64_t m = 1, n = 1, k = 1;
+    int kernel = 0; // 0 = stream, 1 = ttgt
+    size_t ws_bytes = 0;
+    // ttgt
+    bool permute_a = false, permute_b = false;
+    std::vector<int32_t> perm_a, perm_b;
+    size_t ws_a_off = 0, ws_b_off = 0, ws_gemm_off = 0, ws_gemm_bytes = 0;
+    // stream kernel parameters (opaque blob, see contract.cu)
+    std::vector<unsigned char> stream_blob;
+    int launches = 1;
+    double flops() const { return 8.0 * double(m) * double(n) * double(k); }
+    double bytes() const
+    {
+        return double(ElemBytes(dtype)) *
+               (double(m) * double(k) + double(k) * double(n) + double(m) * double(n));
+    }
+};
+
+int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
+                     int rank_b, const int64_t *extent_b, const int32_t *modes_b,
+                     ContractPlan *plan);
+int LaunchContract(const ContractPlan &plan, const void *a, const void *b, void *c, void *ws,
+                   cudaStream_t stream);
+
+// ---- elementwise ---------------------------------------------------------------------------------
+int LaunchAdd(int dtype, int64_t n, const void *a, const void *b, void *c, cudaStream_t stream);
+int LaunchConj(int dtype, int64_t n, const void *in, void *out, cudaStream_t stream);
+int LaunchSlice(int dtype, const void *in, void *out, int rank, const int64_t *extent, int axis,
+                int64_t value, cudaStream_t stream);
+
+} // namespace jb

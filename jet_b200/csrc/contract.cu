@@ -1,0 +1,741 @@
+// K2 — pairwise contraction kernels and their planner.
+//
+// Replaces Tensor::ContractTensors (reference: include/jet/Tensor.hpp:709-752) =
+// Transpose(A) + Transpose(B) + cblas_{c,z}gemm/gemv/dotu (include/jet/TensorHelpers.hpp:131-168).
+//
+// Two kernel families:
+//
+//  (0) StreamContractKernel — the workhorse.  In tensor-network paths one operand is almost always
+//      tiny (<= 4096 elements; 99 % of the traffic of the Sycamore m10/m12 paths) and the GEMM is
+//      extremely skinny (K, N <= 16, M up to 2^27).  The small ("resident") operand is gathered
+//      once per CTA into shared memory as a K x Y matrix; the big ("streamed") operand is read
+//      exactly once straight from its ORIGINAL layout — the index permutation of the reference's
+//      Transpose() is folded into the load addresses (bit insertion for the contracted indices) —
+//      and the output is written exactly once, already in the reference's (left ++ right) order.
+//      HBM traffic = the algorithmic minimum sizeof(T)*(MK + KN + MN).  FP32 (FP64 for c128)
+//      FMA with full-precision accumulation: bandwidth-bound, tensor cores would not help.
+//
+//  (1) TTGT — permute A and B with K1 into a workspace, then a dense row-major complex GEMM
+//      (GemmKernel, FP32/FP64 FMA, shared-memory tiled, deterministic split-K).  Used when both
+//      operands are large, for non-power-of-two extents, and for the GEMV / DOTU corners.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace jb {
+
+// =================================================================================================
+// Stream kernel
+// =================================================================================================
+struct StreamParams {
+    int log_x, log_k, log_y;
+    int out_x_shift, out_y_shift;
+    long long x_count;
+    uint8_t cs[16]; // streamed-operand address bit of k bit q (ascending)
+    uint8_t rk[16]; // resident-operand address bit of k bit q
+    uint8_t ry[16]; // resident-operand address bit of y bit q (ascending)
+};
+
+namespace {
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamMaxResident = 4096;
+
+template <typename R> struct Cx;
+template <> struct Cx<float> {
+    using type = float2;
+};
+template <> struct Cx<double> {
+    using type = double2;
+};
+
+template <typename C> __device__ __forceinline__ void CFma(C &acc, const C a, const C b)
+{
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+
+__device__ __forceinline__ unsigned long long ScatterBits(unsigned long long x, const uint8_t *dst,
+                                                          int nbits)
+{
+    unsigned long long r = 0;
+    for (int q = 0; q < nbits; q++)
+        r |= ((x >> q) & 1ull) << dst[q];
+    return r;
+}
+
+// insert a zero bit at each position cs[0] < cs[1] < ... of x
+__device__ __forceinline__ unsigned long long InsertZeros(unsigned long long x, const uint8_t *cs,
+                                                          int c)
+{
+    for (int q = 0; q < c; q++) {
+        const unsigned long long low = x & ((1ull << cs[q]) - 1ull);
+        x = ((x ^ low) << 1) | low;
+    }
+    return x;
+}
+
+// KC: k values held in registers at once; NR: outputs per thread per pass; XT: x values per thread
+template <typename R, int KC, int NR, int XT>
+__global__ void __launch_bounds__(kStreamThreads)
+    StreamContractKernel(const typename Cx<R>::type *__restrict__ S,
+                         const typename Cx<R>::type *__restrict__ Rsd,
+                         typename Cx<R>::type *__restrict__ out,
+                         const __grid_constant__ StreamParams p)
+{
+    using C = typename Cx<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *Rm = reinterpret_cast<C *>(smem_raw); // [K][Y]
+
+    const int tid = threadIdx.x;
+    const int K = 1 << p.log_k;
+    const int Y = 1 << p.log_y;
+
+    // resident operand -> shared memory, as the K x Y matrix the streamed operand expects
+    for (int e = tid; e < K * Y; e += kStreamThreads) {
+        const unsigned k = e >> p.log_y;
+        const unsigned y = e & (Y - 1);
+        const unsigned long long addr = ScatterBits(k, p.rk, p.log_k) | ScatterBits(y, p.ry, p.log_y);
+        Rm[e] = __ldg(Rsd + addr);
+    }
+
+    // address offset of the low log2(KC) bits of k (loop invariant)
+    unsigned long long koff_lo[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) {
+        unsigned long long r = 0;
+#pragma unroll
+        for (int q = 0; (1 << q) < KC; q++)
+            if (kk & (1 << q))
+                r |= 1ull << p.cs[q];
+        koff_lo[kk] = r;
+    }
+    constexpr int kLogKC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : (KC == 8) ? 3 : 4;
+    const int n_kchunks = K / KC;
+    __syncthreads();
+
+    const long long tile = static_cast<long long>(kStreamThreads) * XT;
+    for (long long x0 = static_cast<long long>(blockIdx.x) * tile; x0 < p.x_count;
+         x0 += static_cast<long long>(gridDim.x) * tile) {
+        long long x[XT];
+        unsigned long long sbase[XT];
+        bool ok[XT];
+#pragma unroll
+        for (int j = 0; j < XT; j++) {
+            x[j] = x0 + j * kStreamThreads + tid;
+            ok[j] = x[j] < p.x_count;
+            sbase[j] = InsertZeros(static_cast<unsigned long long>(ok[j] ? x[j] : 0), p.cs, p.log_k);
+        }
+        C a[XT][KC];
+        for (int y0 = 0; y0 < Y; y0 += NR) {
+            C acc[XT][NR];
+#pragma unroll
+            for (int j = 0; j < XT; j++)
+#pragma unroll
+                for (int yy = 0; yy < NR; yy++)
+                    acc[j][yy] = C{R(0), R(0)};
+            for (int kc = 0; kc < n_kchunks; kc++) {
+                if (n_kchunks > 1 || y0 == 0) {
+                    const unsigned long long khi =
+                        ScatterBits(static_cast<unsigned long long>(kc), p.cs + kLogKC,
+                                    p.log_k - kLogKC);
+#pragma unroll
+                    for (int j = 0; j < XT; j++)
+#pragma unroll
+                        for (int kk = 0; kk < KC; kk++)
+                            a[j][kk] = ok[j] ? __ldg(S + (sbase[j] | khi | koff_lo[kk]))
+                                             : C{R(0), R(0)};
+                }
+                const C *rrow = Rm + (kc * KC) * Y + y0;
+#pragma unroll
+                for (int kk = 0; kk < KC; kk++) {
+#pragma unroll
+                    for (int yy = 0; yy < NR; yy++) {
+                        const C r = rrow[kk * Y + yy];
+#pragma unroll
+                        for (int j = 0; j < XT; j++)
+                            CFma(acc[j][yy], a[j][kk], r);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < XT; j++) {
+                if (!ok[j])
+                    continue;
+                if (p.out_y_shift == 0) {
+                    C *dst = out + ((static_cast<unsigned long long>(x[j]) << p.out_x_shift) + y0);
+                    if constexpr (sizeof(C) == 8 && NR >= 2) {
+#pragma unroll
+                        for (int yy = 0; yy < NR; yy += 2) {
+                            float4 v = make_float4(acc[j][yy].x, acc[j][yy].y, acc[j][yy + 1].x,
+                                                   acc[j][yy + 1].y);
+                            *reinterpret_cast<float4 *>(dst + yy) = v;
+                        }
+                    }
+                    else {
+#pragma unroll
+                        for (int yy = 0; yy < NR; yy++)
+                            dst[yy] = acc[j][yy];
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int yy = 0; yy < NR; yy++)
+                        out[(static_cast<unsigned long long>(y0 + yy) << p.out_y_shift) +
+                            static_cast<unsigned long long>(x[j])] = acc[j][yy];
+                }
+            }
+        }
+    }
+}
+
+template <typename R, int KC, int NR>
+int LaunchStreamT(const StreamParams &p, const void *s, const void *r, void *out,
+                  cudaStream_t stream)
+{
+    using C = typename Cx<R>::type;
+    constexpr int XT = sizeof(R) == 4 ? 2 : 1;
+    const long long tile = static_cast<long long>(kStreamThreads) * XT;
+    const long long tiles = (p.x_count + tile - 1) / tile;
+    const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(NumSMs()) * 4));
+    const size_t smem = sizeof(C) << (p.log_k + p.log_y);
+    auto kernel = StreamContractKernel<R, KC, NR, XT>;
+    if (smem > 48 * 1024) {
+        JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    }
+    kernel<<<grid, kStreamThreads, smem, stream>>>(static_cast<const C *>(s),
+                                                   static_cast<const C *>(r),
+                                                   static_cast<C *>(out), p);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename R, int KC>
+int LaunchStreamK(const StreamParams &p, const void *s, const void *r, void *out,
+                  cudaStream_t stream)
+{
+    const int y = 1 << p.log_y;
+    if (y >= 8)
+        return LaunchStreamT<R, KC, 8>(p, s, r, out, stream);
+    if (y == 4)
+        return LaunchStreamT<R, KC, 4>(p, s, r, out, stream);
+    if (y == 2)
+        return LaunchStreamT<R, KC, 2>(p, s, r, out, stream);
+    return LaunchStreamT<R, KC, 1>(p, s, r, out, stream);
+}
+
+template <typename R>
+int LaunchStream(const StreamParams &p, const void *s, const void *r, void *out,
+                 cudaStream_t stream)
+{
+    const int k = 1 << p.log_k;
+    if (k >= 8)
+        return LaunchStreamK<R, 8>(p, s, r, out, stream);
+    if (k == 4)
+        return LaunchStreamK<R, 4>(p, s, r, out, stream);
+    if (k == 2)
+        return LaunchStreamK<R, 2>(p, s, r, out, stream);
+    return LaunchStreamK<R, 1>(p, s, r, out, stream);
+}
+
+// =================================================================================================
+// Dense row-major complex GEMM (alpha = 1, beta = 0), optional deterministic split-K
+// =================================================================================================
+template <typename R, int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+    GemmKernel(const typename Cx<R>::type *__restrict__ A, const typename Cx<R>::type *__restrict__ B,
+               typename Cx<R>::type *__restrict__ Cout, long long M, long long N, long long K,
+               long long k_per_split)
+{
+    using C = typename Cx<R>::type;
+    constexpr int NT = (BM / TM) * (BN / TN);
+    __shared__ C As[BK][BM + 1];
+    __shared__ C Bs[BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN);
+    const int ty = tid / (BN / TN);
+    const long long tiles_n = (N + BN - 1) / BN;
+    const long long m0 = (static_cast<long long>(blockIdx.x) / tiles_n) * BM;
+    const long long n0 = (static_cast<long long>(blockIdx.x) % tiles_n) * BN;
+    const long long kb = static_cast<long long>(blockIdx.y) * k_per_split;
+    const long long ke = min(K, kb + k_per_split);
+
+    C acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++)
+            acc[i][j] = C{R(0), R(0)};
+
+    for (long long k0 = kb; k0 < ke; k0 += BK) {
+        // A tile: BM x BK, contiguous along k
+        for (int e = tid; e < BM * BK; e += NT) {
+            const int mm = e / BK, kk = e % BK;
+            const long long m = m0 + mm, k = k0 + kk;
+            As[kk][mm] = (m < M && k < ke) ? __ldg(A + m * K + k) : C{R(0), R(0)};
+        }
+        // B tile: BK x BN, contiguous along n
+        for (int e = tid; e < BK * BN; e += NT) {
+            const int kk = e / BN, nn = e % BN;
+            const long long n = n0 + nn, k = k0 + kk;
+            Bs[kk][nn] = (n < N && k < ke) ? __ldg(B + k * N + n) : C{R(0), R(0)};
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            C a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+                a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; j++)
+                b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++)
+                    CFma(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+    C *dst = Cout + static_cast<long long>(blockIdx.y) * M * N;
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        const long long m = m0 + ty * TM + i;
+        if (m >= M)
+            continue;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            const long long n = n0 + tx * TN + j;
+            if (n < N)
+                dst[m * N + n] = acc[i][j];
+        }
+    }
+}
+
+// sum the split-K partials in a fixed order (deterministic), accumulating in double
+template <typename R>
+__global__ void __launch_bounds__(256)
+    SplitKReduceKernel(const typename Cx<R>::type *__restrict__ partial,
+                       typename Cx<R>::type *__restrict__ out, long long mn, int splits)
+{
+    using C = typename Cx<R>::type;
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < mn;
+         i += step) {
+        double re = 0.0, im = 0.0;
+        for (int z = 0; z < splits; z++) {
+            const C v = partial[static_cast<long long>(z) * mn + i];
+            re += static_cast<double>(v.x);
+            im += static_cast<double>(v.y);
+        }
+        out[i] = C{static_cast<R>(re), static_cast<R>(im)};
+    }
+}
+
+struct GemmConfig {
+    bool skinny;
+    int bm, bn;
+    int splits;
+    long long k_per_split;
+};
+
+GemmConfig ChooseGemm(int64_t m, int64_t n, int64_t k)
+{
+    GemmConfig c;
+    c.skinny = (m <= 16 || n <= 32) && (m * n <= 64 * 64 * 4);
+    c.bm = c.skinny ? 16 : 64;
+    c.bn = c.skinny ? 32 : 64;
+    const long long tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn);
+    const long long target = static_cast<long long>(NumSMs()) * 4;
+    long long splits = 1;
+    if (tiles < target && k >= 2048) {
+        splits = std::min<long long>(target / std::max<long long>(tiles, 1), k / 512);
+        splits = std::max<long long>(splits, 1);
+    }
+    long long kps = (k + splits - 1) / splits;
+    kps = ((kps + 31) / 32) * 32;
+    splits = (k + kps - 1) / kps;
+    c.splits = static_cast<int>(std::max<long long>(splits, 1));
+    c.k_per_split = kps;
+    return c;
+}
+
+template <typename R>
+int LaunchGemmT(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws,
+                size_t ws_bytes, cudaStream_t stream)
+{
+    using C = typename Cx<R>::type;
+    const GemmConfig cfg = ChooseGemm(m, n, k);
+    C *dst = static_cast<C *>(c);
+    if (cfg.splits > 1) {
+        const size_t need = sizeof(C) * static_cast<size_t>(cfg.splits) * m * n;
+        JB_REQUIRE(ws != nullptr && ws_bytes >= need, "gemm: split-K workspace too small");
+        dst = static_cast<C *>(ws);
+    }
+    const long long tiles = ((n + cfg.bn - 1) / cfg.bn) * ((m + cfg.bm - 1) / cfg.bm);
+    JB_REQUIRE(tiles < (1ll << 31) && cfg.splits <= 65535, "gemm: problem too large for the dense kernel");
+    dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(cfg.splits), 1);
+    if (cfg.skinny) {
+        GemmKernel<R, 16, 32, 16, 2, 2><<<grid, 128, 0, stream>>>(
+            static_cast<const C *>(a), static_cast<const C *>(b), dst, m, n, k, cfg.k_per_split);
+    }
+    else {
+        GemmKernel<R, 64, 64, 8, 4, 4><<<grid, 256, 0, stream>>>(
+            static_cast<const C *>(a), static_cast<const C *>(b), dst, m, n, k, cfg.k_per_split);
+    }
+    JB_CUDA(cudaGetLastError());
+    if (cfg.splits > 1) {
+        const long long mn = m * n;
+        const int rgrid = static_cast<int>(std::min<long long>((mn + 255) / 256, NumSMs() * 8ll));
+        SplitKReduceKernel<R><<<rgrid, 256, 0, stream>>>(static_cast<const C *>(ws),
+                                                         static_cast<C *>(c), mn, cfg.splits);
+        JB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// =================================================================================================
+// Elementwise kernels
+// =================================================================================================
+template <typename C>
+__global__ void __launch_bounds__(256)
+    AddKernel(const C *__restrict__ a, const C *__restrict__ b, C *__restrict__ c, long long n)
+{
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += step) {
+        const C x = a[i], y = b[i];
+        c[i] = C{x.x + y.x, x.y + y.y};
+    }
+}
+
+template <typename C>
+__global__ void __launch_bounds__(256)
+    ConjKernel(const C *__restrict__ a, C *__restrict__ c, long long n)
+{
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += step) {
+        const C x = a[i];
+        c[i] = C{x.x, -x.y};
+    }
+}
+
+// out[o][i] = in[o][value][i]
+template <typename V>
+__global__ void __launch_bounds__(256)
+    SliceKernel(const V *__restrict__ in, V *__restrict__ out, long long outer, long long extent,
+                long long inner, long long value)
+{
+    const long long total = outer * inner;
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += step) {
+        const long long o = i / inner, r = i % inner;
+        out[i] = in[(o * extent + value) * inner + r];
+    }
+}
+
+int GridFor(long long n)
+{
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, NumSMs() * 16ll)));
+}
+
+} // namespace
+
+// =================================================================================================
+// Host API
+// =================================================================================================
+size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k)
+{
+    const GemmConfig cfg = ChooseGemm(m, n, k);
+    if (cfg.splits <= 1)
+        return 0;
+    return ElemBytes(dtype) * static_cast<size_t>(cfg.splits) * m * n;
+}
+
+int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c,
+               void *ws, size_t ws_bytes, cudaStream_t stream)
+{
+    JB_REQUIRE(m >= 1 && n >= 1 && k >= 1, "gemm: dimensions must be positive");
+    if (dtype == JB_C64)
+        return LaunchGemmT<float>(m, n, k, a, b, c, ws, ws_bytes, stream);
+    if (dtype == JB_C128)
+        return LaunchGemmT<double>(m, n, k, a, b, c, ws, ws_bytes, stream);
+    return Fail("gemm: unknown dtype");
+}
+
+int LaunchAdd(int dtype, int64_t n, const void *a, const void *b, void *c, cudaStream_t stream)
+{
+    if (n <= 0)
+        return 0;
+    if (dtype == JB_C64)
+        AddKernel<float2><<<GridFor(n), 256, 0, stream>>>(static_cast<const float2 *>(a),
+                                                         static_cast<const float2 *>(b),
+                                                         static_cast<float2 *>(c), n);
+    else
+        AddKernel<double2><<<GridFor(n), 256, 0, stream>>>(static_cast<const double2 *>(a),
+                                                          static_cast<const double2 *>(b),
+                                                          static_cast<double2 *>(c), n);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int LaunchConj(int dtype, int64_t n, const void *in, void *out, cudaStream_t stream)
+{
+    if (n <= 0)
+        return 0;
+    if (dtype == JB_C64)
+        ConjKernel<float2><<<GridFor(n), 256, 0, stream>>>(static_cast<const float2 *>(in),
+                                                          static_cast<float2 *>(out), n);
+    else
+        ConjKernel<double2><<<GridFor(n), 256, 0, stream>>>(static_cast<const double2 *>(in),
+                                                           static_cast<double2 *>(out), n);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int LaunchSlice(int dtype, const void *in, void *out, int rank, const int64_t *extent, int axis,
+                int64_t value, cudaStream_t stream)
+{
+    JB_REQUIRE(axis >= 0 && axis < rank, "slice: axis out of range");
+    JB_REQUIRE(value >= 0 && value < extent[axis], "slice: value out of range");
+    long long outer = 1, inner = 1;
+    for (int i = 0; i < axis; i++)
+        outer *= extent[i];
+    for (int i = axis + 1; i < rank; i++)
+        inner *= extent[i];
+    const long long total = outer * inner;
+    if (dtype == JB_C64)
+        SliceKernel<uint2><<<GridFor(total), 256, 0, stream>>>(static_cast<const uint2 *>(in),
+                                                              static_cast<uint2 *>(out), outer,
+                                                              extent[axis], inner, value);
+    else
+        SliceKernel<uint4><<<GridFor(total), 256, 0, stream>>>(static_cast<const uint4 *>(in),
+                                                              static_cast<uint4 *>(out), outer,
+                                                              extent[axis], inner, value);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Contraction planning: index algebra of Tensor::ContractTensors (include/jet/Tensor.hpp:714-741)
+// -------------------------------------------------------------------------------------------------
+int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
+                     int rank_b, const int64_t *extent_b, const int32_t *modes_b,
+                     ContractPlan *plan)
+{
+    JB_REQUIRE(dtype == JB_C64 || dtype == JB_C128, "contract: unknown dtype");
+    JB_REQUIRE(rank_a >= 0 && rank_a <= JB_MAX_RANK && rank_b >= 0 && rank_b <= JB_MAX_RANK,
+               "contract: rank out of range");
+    ContractPlan &P = *plan;
+    P = ContractPlan();
+    P.dtype = dtype;
+    P.rank_a = rank_a;
+    P.rank_b = rank_b;
+    P.extent_a.assign(extent_a, extent_a + rank_a);
+    P.extent_b.assign(extent_b, extent_b + rank_b);
+    P.modes_a.assign(modes_a, modes_a + rank_a);
+    P.modes_b.assign(modes_b, modes_b + rank_b);
+    for (int i = 0; i < rank_a; i++)
+        for (int j = i + 1; j < rank_a; j++)
+            JB_REQUIRE(modes_a[i] != modes_a[j], "contract: repeated mode in A");
+    for (int i = 0; i < rank_b; i++)
+        for (int j = i + 1; j < rank_b; j++)
+            JB_REQUIRE(modes_b[i] != modes_b[j], "contract: repeated mode in B");
+
+    auto find = [](const int32_t *modes, int rank, int32_t m) {
+        for (int i = 0; i < rank; i++)
+            if (modes[i] == m)
+                return i;
+        return -1;
+    };
+    std::vector<int> left, right, common_a, common_b; // axis positions
+    for (int i = 0; i < rank_a; i++) {
+        const int j = find(modes_b, rank_b, modes_a[i]);
+        if (j < 0)
+            left.push_back(i);
+        else {
+            common_a.push_back(i);
+            common_b.push_back(j);
+        }
+    }
+    for (int j = 0; j < rank_b; j++)
+        if (find(modes_a, rank_a, modes_b[j]) < 0)
+            right.push_back(j);
+
+    bool pow2 = true;
+    P.m = P.n = P.k = 1;
+    for (int i : left) {
+        P.m *= extent_a[i];
+        P.modes_c.push_back(modes_a[i]);
+        P.extent_c.push_back(extent_a[i]);
+    }
+    for (int j : right) {
+        P.n *= extent_b[j];
+        P.modes_c.push_back(modes_b[j]);
+        P.extent_c.push_back(extent_b[j]);
+    }
+    for (size_t q = 0; q < common_a.size(); q++) {
+        // the reference takes common extents from A without cross-checking B
+        // (Tensor.hpp:727-730); a mismatch is an error here
+        JB_REQUIRE(extent_a[common_a[q]] == extent_b[common_b[q]],
+                   "contract: contracted extents differ between A and B");
+        P.k *= extent_a[common_a[q]];
+    }
+    P.rank_c = static_cast<int>(P.modes_c.size());
+    JB_REQUIRE(P.rank_c <= JB_MAX_RANK, "contract: output rank out of range");
+    for (int i = 0; i < rank_a; i++)
+        pow2 = pow2 && IsPow2(extent_a[i]);
+    for (int j = 0; j < rank_b; j++)
+        pow2 = pow2 && IsPow2(extent_b[j]);
+
+    const int64_t size_a = P.m * P.k, size_b = P.k * P.n;
+
+    // ---- stream kernel: one operand small, all extents powers of two ----------------------------
+    if (pow2 && std::min(size_a, size_b) <= kStreamMaxResident) {
+        const bool stream_a = size_a >= size_b; // A streamed, B resident
+        const int rs = stream_a ? rank_a : rank_b;
+        const int rr = stream_a ? rank_b : rank_a;
+        const int64_t *es = stream_a ? extent_a : extent_b;
+        const int64_t *er = stream_a ? extent_b : extent_a;
+        const std::vector<int> &cs_axes = stream_a ? common_a : common_b;
+        const std::vector<int> &cr_axes = stream_a ? common_b : common_a;
+        const std::vector<int> &free_r = stream_a ? right : left;
+        // bit layout of both operands (last axis lowest)
+        std::vector<int> lo_s(rs), lo_r(rr);
+        int ns = 0, nr = 0;
+        for (int i = rs - 1; i >= 0; i--) {
+            lo_s[i] = ns;
+            ns += Log2(es[i]);
+        }
+        for (int i = rr - 1; i >= 0; i--) {
+            lo_r[i] = nr;
+            nr += Log2(er[i]);
+        }
+        // k bits, ascending in the streamed operand's address
+        struct KB {
+            int s_bit, r_bit;
+        };
+        std::vector<KB> kb;
+        for (size_t q = 0; q < cs_axes.size(); q++) {
+            const int bits = Log2(es[cs_axes[q]]);
+            for (int bbit = 0; bbit < bits; bbit++)
+                kb.push_back({lo_s[cs_axes[q]] + bbit, lo_r[cr_axes[q]] + bbit});
+        }
+        std::sort(kb.begin(), kb.end(), [](const KB &x, const KB &y) { return x.s_bit < y.s_bit; });
+        std::vector<int> yb; // resident free bits ascending
+        for (int ax : free_r) {
+            const int bits = Log2(er[ax]);
+            for (int bbit = 0; bbit < bits; bbit++)
+                yb.push_back(lo_r[ax] + bbit);
+        }
+        std::sort(yb.begin(), yb.end());
+        if (kb.size() <= 12 && yb.size() <= 12 && ns <= 62) {
+            StreamParams sp;
+            std::memset(&sp, 0, sizeof(sp));
+            sp.log_k = static_cast<int>(kb.size());
+            sp.log_y = static_cast<int>(yb.size());
+            sp.log_x = ns - sp.log_k;
+            sp.x_count = 1ll << sp.log_x;
+            for (int q = 0; q < sp.log_k; q++) {
+                sp.cs[q] = static_cast<uint8_t>(kb[q].s_bit);
+                sp.rk[q] = static_cast<uint8_t>(kb[q].r_bit);
+            }
+            for (int q = 0; q < sp.log_y; q++)
+                sp.ry[q] = static_cast<uint8_t>(yb[q]);
+            if (stream_a) { // C = (x << log_y) | y
+                sp.out_x_shift = sp.log_y;
+                sp.out_y_shift = 0;
+            }
+            else { // C = (y << log_x) | x
+                sp.out_x_shift = 0;
+                sp.out_y_shift = sp.log_x;
+            }
+            P.kernel = 0;
+            P.ws_bytes = 0;
+            P.launches = 1;
+            P.stream_blob.resize(sizeof(sp) + 1);
+            std::memcpy(P.stream_blob.data(), &sp, sizeof(sp));
+            P.stream_blob[sizeof(sp)] = stream_a ? 1 : 0;
+            return 0;
+        }
+    }
+
+    // ---- TTGT -----------------------------------------------------------------------------------
+    P.kernel = 1;
+    P.perm_a.clear();
+    P.perm_b.clear();
+    for (int i : left)
+        P.perm_a.push_back(i);
+    for (int i : common_a)
+        P.perm_a.push_back(i);
+    for (int j : common_b)
+        P.perm_b.push_back(j);
+    for (int j : right)
+        P.perm_b.push_back(j);
+    P.permute_a = P.permute_b = false;
+    for (int i = 0; i < rank_a; i++)
+        P.permute_a = P.permute_a || P.perm_a[i] != i;
+    for (int j = 0; j < rank_b; j++)
+        P.permute_b = P.permute_b || P.perm_b[j] != j;
+    const size_t eb = ElemBytes(dtype);
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t off = 0;
+    P.launches = 1;
+    if (P.permute_a) {
+        P.ws_a_off = off;
+        off += align(eb * static_cast<size_t>(size_a));
+        P.launches++;
+    }
+    if (P.permute_b) {
+        P.ws_b_off = off;
+        off += align(eb * static_cast<size_t>(size_b));
+        P.launches++;
+    }
+    P.ws_gemm_off = off;
+    P.ws_gemm_bytes = GemmWorkspaceBytes(dtype, P.m, P.n, P.k);
+    if (P.ws_gemm_bytes > 0)
+        P.launches++;
+    off += align(P.ws_gemm_bytes);
+    P.ws_bytes = off;
+    return 0;
+}
+
+int LaunchContract(const ContractPlan &P, const void *a, const void *b, void *c, void *ws,
+                   cudaStream_t stream)
+{
+    if (P.kernel == 0) {
+        StreamParams sp;
+        std::memcpy(&sp, P.stream_blob.data(), sizeof(sp));
+        const bool stream_a = P.stream_blob[sizeof(sp)] != 0;
+        const void *s = stream_a ? a : b;
+        const void *r = stream_a ? b : a;
+        if (P.dtype == JB_C64)
+            return LaunchStream<float>(sp, s, r, c, stream);
+        return LaunchStream<double>(sp, s, r, c, stream);
+    }
+    JB_REQUIRE(P.ws_bytes == 0 || ws != nullptr, "contract: workspace required");
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    const void *at = a, *bt = b;
+    if (P.permute_a) {
+        JB_TRY(LaunchPermute(P.dtype, a, w + P.ws_a_off, P.rank_a, P.extent_a.data(),
+                             P.perm_a.data(), stream));
+        at = w + P.ws_a_off;
+    }
+    if (P.permute_b) {
+        JB_TRY(LaunchPermute(P.dtype, b, w + P.ws_b_off, P.rank_b, P.extent_b.data(),
+                             P.perm_b.data(), stream));
+        bt = w + P.ws_b_off;
+    }
+    return LaunchGemm(P.dtype, P.m, P.n, P.k, at, bt, c, w ? w + P.ws_gemm_off : nullptr,
+                      P.ws_gemm_bytes, stream);
+}
+
+} // namespace jb

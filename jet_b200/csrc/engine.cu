@@ -1,0 +1,797 @@
+// Contraction plan: a whole (sliced) tensor network + path resident on one GPU.
+//
+// Replaces the execution half of TaskBasedContractor (reference:
+// include/jet/TaskBasedContractor.hpp:162-322): instead of one host task per contraction that
+// allocates, zero-fills and page-faults a fresh std::vector (include/jet/Tensor.hpp:58-60,743),
+//   * leaves are uploaded once into a device arena;
+//   * TensorNetwork::SliceIndices (include/jet/TensorNetwork.hpp:210-284) becomes a device-side
+//     view: a tiny kernel gathers the sliced leaves for the current slice id, so 2^s slices never
+//     exist as 2^s host copies of the network (examples/paper_benchmarks/CPU/jet_cpu_m10/
+//     jet_sliced.cpp:69-75);
+//   * slice-independent steps (the reference's de-duplication by task name,
+//     TaskBasedContractor.hpp:216-222) run once; the per-slice steps are captured into ONE CUDA
+//     graph that is re-launched per slice with no host synchronisation in between;
+//   * intermediates get arena offsets from their lifetimes at plan time (AddDeletionTasks,
+//     TaskBasedContractor.hpp:290-315, becomes a plan-time analysis);
+//   * the reduction over slices (AddReductionTask, TaskBasedContractor.hpp:258-280) is a
+//     double-precision accumulator on the device, summed in slice order (deterministic).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+
+#include "common.cuh"
+
+namespace jb {
+namespace {
+
+// ---- offset allocator (plan-time simulation of the arena) ---------------------------------------
+class OffsetAllocator {
+  public:
+    size_t Alloc(size_t bytes)
+    {
+        bytes = Align(bytes);
+        auto best = free_.end();
+        for (auto it = free_.begin(); it != free_.end(); ++it) {
+            if (it->second >= bytes && (best == free_.end() || it->second < best->second))
+                best = it;
+        }
+        if (best != free_.end()) {
+            const size_t off = best->first, sz = best->second;
+            free_.erase(best);
+            if (sz > bytes)
+                free_[off + bytes] = sz - bytes;
+            return off;
+        }
+        // extend the top (merging with a trailing free block)
+        if (!free_.empty()) {
+            auto last = std::prev(free_.end());
+            if (last->first + last->second == top_) {
+                const size_t off = last->first;
+                free_.erase(last);
+                top_ = off + bytes;
+                peak_ = std::max(peak_, top_);
+                return off;
+            }
+        }
+        const size_t off = top_;
+        top_ += bytes;
+        peak_ = std::max(peak_, top_);
+        return off;
+    }
+    void Free(size_t off, size_t bytes)
+    {
+        bytes = Align(bytes);
+        auto it = free_.emplace(off, bytes).first;
+        auto next = std::next(it);
+        if (next != free_.end() && it->first + it->second == next->first) {
+            it->second += next->second;
+            free_.erase(next);
+        }
+        if (it != free_.begin()) {
+            auto prev = std::prev(it);
+            if (prev->first + prev->second == it->first) {
+                prev->second += it->second;
+                free_.erase(it);
+            }
+        }
+    }
+    size_t Peak() const { return peak_; }
+    static size_t Align(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~size_t(511); }
+
+  private:
+    std::map<size_t, size_t> free_;
+    size_t top_ = 0, peak_ = 0;
+};
+
+// ---- device-side slice selection -----------------------------------------------------------------
+constexpr int kSliceMaxRem = 16;
+constexpr int kSliceMaxSl = 8;
+
+struct SliceLeafDesc {
+    long long src_off; // element offset of the unsliced leaf in the arena
+    long long dst_off; // element offset of the sliced view
+    long long out_elems;
+    int n_rem, n_sl;
+    long long rem_ext[kSliceMaxRem], rem_stride[kSliceMaxRem];
+    long long sl_div[kSliceMaxSl], sl_dim[kSliceMaxSl], sl_stride[kSliceMaxSl];
+};
+
+struct DeviceState {
+    long long next_id;  // slice id of the next graph launch (sequential mode)
+    long long ordinal;  // slices accumulated since reset
+    long long list_pos; // >= 0: take ids from the list
+};
+
+__device__ __forceinline__ long long CurrentSlice(const DeviceState *st, const long long *list)
+{
+    return st->list_pos >= 0 ? list[st->list_pos] : st->next_id;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(128)
+    SliceLeavesKernel(V *__restrict__ arena, const SliceLeafDesc *__restrict__ descs,
+                      const DeviceState *__restrict__ st, const long long *__restrict__ list)
+{
+    const SliceLeafDesc &d = descs[blockIdx.x];
+    const long long sid = CurrentSlice(st, list);
+    long long base = d.src_off;
+    for (int s = 0; s < d.n_sl; s++)
+        base += ((sid / d.sl_div[s]) % d.sl_dim[s]) * d.sl_stride[s];
+    for (long long e = threadIdx.x; e < d.out_elems; e += blockDim.x) {
+        long long rem = e, off = base;
+        for (int j = d.n_rem - 1; j >= 0; j--) {
+            off += (rem % d.rem_ext[j]) * d.rem_stride[j];
+            rem /= d.rem_ext[j];
+        }
+        arena[d.dst_off + e] = arena[off];
+    }
+}
+
+template <typename C>
+__global__ void __launch_bounds__(256)
+    AccumulateKernel(const C *__restrict__ result, double2 *__restrict__ acc, C *__restrict__ store,
+                     long long elems, long long store_cap, DeviceState *st)
+{
+    const long long ordinal = st->ordinal;
+    for (long long i = threadIdx.x; i < elems; i += blockDim.x) {
+        const C v = result[i];
+        double2 a = acc[i];
+        a.x += static_cast<double>(v.x);
+        a.y += static_cast<double>(v.y);
+        acc[i] = a;
+        if (store != nullptr && ordinal < store_cap)
+            store[ordinal * elems + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->ordinal = ordinal + 1;
+        if (st->list_pos >= 0)
+            st->list_pos = st->list_pos + 1;
+        else
+            st->next_id = st->next_id + 1;
+    }
+}
+
+__global__ void SetStateKernel(DeviceState *st, long long next_id, long long list_pos,
+                               int reset_ordinal)
+{
+    st->next_id = next_id;
+    st->list_pos = list_pos;
+    if (reset_ordinal)
+        st->ordinal = 0;
+}
+
+struct Node {
+    std::vector<int32_t> modes;
+    std::vector<int64_t> extent;
+    int64_t elems = 1;
+    bool slice_dep = false; // depends on the slice id
+    bool is_leaf = false;
+    size_t offset = 0; // byte offset in the arena of the tensor the steps read
+    size_t raw_offset = 0; // leaves: byte offset of the unsliced data
+    int last_use = -1;     // last step (in execution order) reading this node
+    bool used_by_slice_step = false;
+};
+
+struct Step {
+    int a, b, c;
+    bool shared;
+    ContractPlan cp;
+};
+
+} // namespace
+} // namespace jb
+
+using namespace jb;
+
+struct jb_plan {
+    int dtype = JB_C64;
+    int device = 0;
+    int flags = 0;
+    size_t eb = 8;
+    int num_leaves = 0;
+    std::vector<Node> nodes;
+    std::vector<Step> steps;
+    std::vector<int> shared_order, slice_order;
+    std::vector<int32_t> sliced_modes;
+    std::vector<int64_t> sliced_dims;
+    int64_t num_slices = 1;
+    std::vector<SliceLeafDesc> slice_descs;
+
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t ws_off = 0, ws_bytes = 0;
+    size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0;
+    int64_t store_cap = 0, list_cap = 0;
+    int64_t result_elems = 1;
+    int result_node = -1;
+
+    cudaStream_t stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool shared_done = false;
+    bool have_run = false;
+    long long *h_list = nullptr;
+    jb_plan_stats_t stats;
+
+    template <typename T> T *At(size_t off) const { return reinterpret_cast<T *>(arena + off); }
+};
+
+namespace {
+
+int EnqueueSliceBody(jb_plan *p)
+{
+    if (!p->slice_descs.empty()) {
+        const int n = static_cast<int>(p->slice_descs.size());
+        if (p->dtype == JB_C64)
+            SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(
+                p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off), p->At<DeviceState>(p->state_off),
+                p->At<long long>(p->list_off));
+        else
+            SliceLeavesKernel<uint4><<<n, 128, 0, p->stream>>>(
+                p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off), p->At<DeviceState>(p->state_off),
+                p->At<long long>(p->list_off));
+        JB_CUDA(cudaGetLastError());
+    }
+    for (int s : p->slice_order) {
+        const Step &st = p->steps[s];
+        JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
+                              p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream));
+    }
+    const bool store = (p->flags & JB_PLAN_STORE_RESULTS) != 0;
+    const void *res = p->arena + p->nodes[p->result_node].offset;
+    if (p->dtype == JB_C64)
+        AccumulateKernel<float2><<<1, 256, 0, p->stream>>>(
+            static_cast<const float2 *>(res), p->At<double2>(p->acc_off),
+            store ? p->At<float2>(p->store_off) : nullptr, p->result_elems, p->store_cap,
+            p->At<DeviceState>(p->state_off));
+    else
+        AccumulateKernel<double2><<<1, 256, 0, p->stream>>>(
+            static_cast<const double2 *>(res), p->At<double2>(p->acc_off),
+            store ? p->At<double2>(p->store_off) : nullptr, p->result_elems, p->store_cap,
+            p->At<DeviceState>(p->state_off));
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int RunShared(jb_plan *p)
+{
+    if (p->shared_done)
+        return 0;
+    for (int s : p->shared_order) {
+        const Step &st = p->steps[s];
+        JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
+                              p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream));
+    }
+    p->shared_done = true;
+    return 0;
+}
+
+int EnsureGraph(jb_plan *p)
+{
+    if (p->graph_exec != nullptr || (p->flags & JB_PLAN_NO_GRAPH))
+        return 0;
+    JB_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = EnqueueSliceBody(p);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
+    if (rc != 0) {
+        if (g)
+            cudaGraphDestroy(g);
+        return rc;
+    }
+    JB_CUDA(ce);
+    p->graph = g;
+    JB_CUDA(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
+    return 0;
+}
+
+int RunSlices(jb_plan *p, long long first, long long list_pos, long long count)
+{
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_TRY(RunShared(p));
+    JB_TRY(EnsureGraph(p));
+    SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), first, list_pos, 0);
+    JB_CUDA(cudaGetLastError());
+    JB_CUDA(cudaEventRecord(p->ev0, p->stream));
+    for (long long i = 0; i < count; i++) {
+        if (p->graph_exec)
+            JB_CUDA(cudaGraphLaunch(p->graph_exec, p->stream));
+        else
+            JB_TRY(EnqueueSliceBody(p));
+    }
+    JB_CUDA(cudaEventRecord(p->ev1, p->stream));
+    p->have_run = true;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
+{
+    JB_REQUIRE(d != nullptr && out != nullptr, "plan: null argument");
+    JB_REQUIRE(d->dtype == JB_C64 || d->dtype == JB_C128, "plan: unknown dtype");
+    JB_REQUIRE(d->num_leaves >= 1, "An empty tensor network cannot be contracted.");
+    JB_CUDA(cudaSetDevice(d->device));
+    std::unique_ptr<jb_plan> up(new jb_plan());
+    jb_plan *p = up.get();
+    p->dtype = d->dtype;
+    p->device = d->device;
+    p->flags = d->flags;
+    p->eb = ElemBytes(d->dtype);
+    p->num_leaves = d->num_leaves;
+    p->sliced_modes.assign(d->sliced_modes, d->sliced_modes + d->num_sliced);
+    const bool keep = (d->flags & JB_PLAN_KEEP_INTERMEDIATES) != 0;
+
+    // ---- nodes ----------------------------------------------------------------------------------
+    std::map<int32_t, int64_t> mode_dim;
+    size_t off = 0;
+    for (int i = 0; i < d->num_leaves; i++) {
+        Node n;
+        n.is_leaf = true;
+        const int r = d->rank[i];
+        JB_REQUIRE(r >= 0 && r <= JB_MAX_RANK, "plan: leaf rank out of range");
+        n.modes.assign(d->mode + off, d->mode + off + r);
+        n.extent.assign(d->extent + off, d->extent + off + r);
+        for (int j = 0; j < r; j++) {
+            JB_REQUIRE(n.extent[j] >= 1, "plan: extents must be positive");
+            n.elems *= n.extent[j];
+            mode_dim[n.modes[j]] = n.extent[j];
+        }
+        off += r;
+        p->nodes.push_back(n);
+    }
+    p->sliced_dims.clear();
+    p->num_slices = 1;
+    for (int32_t m : p->sliced_modes) {
+        auto it = mode_dim.find(m);
+        JB_REQUIRE(it != mode_dim.end(), "Sliced index does not exist.");
+        p->sliced_dims.push_back(it->second);
+        p->num_slices *= it->second;
+    }
+    auto is_sliced = [&](int32_t m) {
+        return std::find(p->sliced_modes.begin(), p->sliced_modes.end(), m) != p->sliced_modes.end();
+    };
+
+    // ---- arena layout: raw leaves, then sliced views ----------------------------------------------
+    OffsetAllocator alloc;
+    for (int i = 0; i < d->num_leaves; i++) {
+        Node &n = p->nodes[i];
+        n.raw_offset = alloc.Alloc(n.elems * p->eb);
+        n.offset = n.raw_offset;
+    }
+    for (int i = 0; i < d->num_leaves; i++) {
+        Node &n = p->nodes[i];
+        std::vector<int> sl_axes;
+        for (size_t j = 0; j < n.modes.size(); j++)
+            if (is_sliced(n.modes[j]))
+                sl_axes.push_back(static_cast<int>(j));
+        if (sl_axes.empty())
+            continue;
+        n.slice_dep = true;
+        SliceLeafDesc sd;
+        std::memset(&sd, 0, sizeof(sd));
+        JB_REQUIRE(sl_axes.size() <= kSliceMaxSl, "plan: too many sliced indices on one leaf");
+        std::vector<int64_t> stride(n.modes.size());
+        int64_t s = 1;
+        for (int j = static_cast<int>(n.modes.size()) - 1; j >= 0; j--) {
+            stride[j] = s;
+            s *= n.extent[j];
+        }
+        std::vector<int32_t> new_modes;
+        std::vector<int64_t> new_ext;
+        int64_t out_elems = 1;
+        for (size_t j = 0; j < n.modes.size(); j++) {
+            if (is_sliced(n.modes[j])) {
+                // digit of this mode inside the slice id: first listed mode is slowest
+                int64_t div = 1;
+                const size_t pos = std::find(p->sliced_modes.begin(), p->sliced_modes.end(), n.modes[j]) -
+                                   p->sliced_modes.begin();
+                for (size_t q = pos + 1; q < p->sliced_modes.size(); q++)
+                    div *= p->sliced_dims[q];
+                sd.sl_div[sd.n_sl] = div;
+                sd.sl_dim[sd.n_sl] = n.extent[j];
+                sd.sl_stride[sd.n_sl] = stride[j];
+                sd.n_sl++;
+            }
+            else {
+                JB_REQUIRE(sd.n_rem < kSliceMaxRem, "plan: sliced leaf rank too large");
+                sd.rem_ext[sd.n_rem] = n.extent[j];
+                sd.rem_stride[sd.n_rem] = stride[j];
+                sd.n_rem++;
+                new_modes.push_back(n.modes[j]);
+                new_ext.push_back(n.extent[j]);
+                out_elems *= n.extent[j];
+            }
+        }
+        sd.out_elems = out_elems;
+        sd.src_off = static_cast<long long>(n.raw_offset / p->eb);
+        n.offset = alloc.Alloc(out_elems * p->eb);
+        sd.dst_off = static_cast<long long>(n.offset / p->eb);
+        n.modes = new_modes;
+        n.extent = new_ext;
+        n.elems = out_elems;
+        p->slice_descs.push_back(sd);
+    }
+
+    // ---- steps: symbolic replay of the path (include/jet/PathInfo.hpp:262-297) --------------------
+    JB_REQUIRE(d->num_steps >= 0, "plan: negative step count");
+    for (int s = 0; s < d->num_steps; s++) {
+        const int a = d->path[2 * s], b = d->path[2 * s + 1];
+        const int cur = static_cast<int>(p->nodes.size());
+        JB_REQUIRE(a >= 0 && a < cur, "Node ID 1 in contraction pair is invalid.");
+        JB_REQUIRE(b >= 0 && b < cur, "Node ID 2 in contraction pair is invalid.");
+        JB_REQUIRE(a != b, "plan: a node cannot be contracted with itself");
+        Step st;
+        st.a = a;
+        st.b = b;
+        st.c = cur;
+        const Node &A = p->nodes[a];
+        const Node &B = p->nodes[b];
+        JB_TRY(MakeContractPlan(p->dtype, static_cast<int>(A.modes.size()), A.extent.data(),
+                                A.modes.data(), static_cast<int>(B.modes.size()), B.extent.data(),
+                                B.modes.data(), &st.cp));
+        st.shared = !(A.slice_dep || B.slice_dep);
+        Node C;
+        C.modes = st.cp.modes_c;
+        C.extent = st.cp.extent_c;
+        C.elems = st.cp.m * st.cp.n;
+        C.slice_dep = !st.shared;
+        p->nodes.push_back(C);
+        p->steps.push_back(st);
+    }
+    p->result_node = static_cast<int>(p->nodes.size()) - 1;
+    p->result_elems = p->nodes[p->result_node].elems;
+    if (d->num_steps > 0)
+        p->nodes[p->result_node].slice_dep = true; // the accumulate step runs per slice
+    // the final step is always executed per slice so the accumulator sees one result per slice
+    if (!p->steps.empty())
+        p->steps.back().shared = false;
+
+    for (size_t s = 0; s < p->steps.size(); s++)
+        (p->steps[s].shared ? p->shared_order : p->slice_order).push_back(static_cast<int>(s));
+
+    // ---- lifetimes in execution order (shared steps first, then per-slice steps) ------------------
+    std::vector<int> exec = p->shared_order;
+    exec.insert(exec.end(), p->slice_order.begin(), p->slice_order.end());
+    for (size_t e = 0; e < exec.size(); e++) {
+        const Step &st = p->steps[exec[e]];
+        p->nodes[st.a].last_use = static_cast<int>(e);
+        p->nodes[st.b].last_use = static_cast<int>(e);
+        if (!st.shared) {
+            p->nodes[st.a].used_by_slice_step = true;
+            p->nodes[st.b].used_by_slice_step = true;
+        }
+    }
+    size_t ws_max = 0;
+    for (size_t e = 0; e < exec.size(); e++) {
+        const Step &st = p->steps[exec[e]];
+        Node &C = p->nodes[st.c];
+        C.offset = alloc.Alloc(C.elems * p->eb);
+        ws_max = std::max(ws_max, st.cp.ws_bytes);
+        if (keep)
+            continue;
+        for (int in : {st.a, st.b}) {
+            Node &I = p->nodes[in];
+            if (I.is_leaf || I.last_use != static_cast<int>(e))
+                continue;
+            // a shared tensor read by per-slice steps must survive every slice
+            const bool producer_shared = !I.slice_dep;
+            if (producer_shared && I.used_by_slice_step)
+                continue;
+            alloc.Free(I.offset, I.elems * p->eb);
+        }
+    }
+    p->ws_bytes = ws_max;
+    p->ws_off = alloc.Alloc(std::max<size_t>(ws_max, 512));
+    p->acc_off = alloc.Alloc(sizeof(double2) * p->result_elems);
+    p->store_cap = (d->flags & JB_PLAN_STORE_RESULTS) ? p->num_slices : 0;
+    if (p->store_cap > 0)
+        p->store_off = alloc.Alloc(p->eb * p->result_elems * p->store_cap);
+    p->state_off = alloc.Alloc(sizeof(DeviceState));
+    p->list_cap = std::max<int64_t>(p->num_slices, 1);
+    p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
+    p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
+    p->arena_bytes = alloc.Peak();
+
+    // ---- device resources ---------------------------------------------------------------------------
+    size_t free_b = 0, total_b = 0;
+    JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (p->arena_bytes > free_b) {
+        return Fail("plan: the contraction needs " + std::to_string(p->arena_bytes >> 20) +
+                    " MiB of device memory but only " + std::to_string(free_b >> 20) +
+                    " MiB are free; slice more indices");
+    }
+    JB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->arena), p->arena_bytes));
+    JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    JB_CUDA(cudaEventCreate(&p->ev0));
+    JB_CUDA(cudaEventCreate(&p->ev1));
+    JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_list), sizeof(long long) * p->list_cap));
+    if (!p->slice_descs.empty())
+        JB_CUDA(cudaMemcpyAsync(p->arena + p->descs_off, p->slice_descs.data(),
+                                sizeof(SliceLeafDesc) * p->slice_descs.size(), cudaMemcpyHostToDevice,
+                                p->stream));
+    JB_CUDA(cudaMemsetAsync(p->arena + p->acc_off, 0, sizeof(double2) * p->result_elems, p->stream));
+    JB_CUDA(cudaMemsetAsync(p->arena + p->state_off, 0, sizeof(DeviceState), p->stream));
+
+    // ---- statistics -----------------------------------------------------------------------------------
+    jb_plan_stats_t &S = p->stats;
+    std::memset(&S, 0, sizeof(S));
+    S.num_slices = p->num_slices;
+    S.result_elems = p->result_elems;
+    const Node &RN = p->nodes[p->result_node];
+    S.result_rank = static_cast<int32_t>(RN.modes.size());
+    for (size_t j = 0; j < RN.modes.size(); j++) {
+        S.result_modes[j] = RN.modes[j];
+        S.result_extent[j] = RN.extent[j];
+    }
+    S.steps_total = static_cast<int32_t>(p->steps.size());
+    S.steps_shared = static_cast<int32_t>(p->shared_order.size());
+    S.launches_per_slice = (p->slice_descs.empty() ? 0 : 1) + 1;
+    for (const Step &st : p->steps) {
+        S.jet_flops_per_slice += 2.0 * double(st.cp.m) * double(st.cp.n) * double(st.cp.k);
+        S.max_step_elems = std::max<int64_t>(S.max_step_elems, st.cp.m * st.cp.n);
+        if (st.shared) {
+            S.flops_shared += st.cp.flops();
+            S.bytes_shared += st.cp.bytes();
+        }
+        else {
+            S.flops_per_slice += st.cp.flops();
+            S.bytes_per_slice += st.cp.bytes();
+            S.launches_per_slice += st.cp.launches;
+            if (st.cp.kernel == 0)
+                S.steps_stream++;
+            else
+                S.steps_ttgt++;
+        }
+    }
+    S.arena_bytes = p->arena_bytes;
+
+    if (d->h_data != nullptr) {
+        const int rc = jb_plan_upload(p, d->h_data);
+        if (rc != 0) {
+            jb_plan_destroy(up.release());
+            return rc;
+        }
+    }
+    *out = up.release();
+    return 0;
+}
+
+int jb_plan_destroy(jb_plan *p)
+{
+    if (p == nullptr)
+        return 0;
+    cudaSetDevice(p->device);
+    if (p->stream)
+        cudaStreamSynchronize(p->stream);
+    if (p->graph_exec)
+        cudaGraphExecDestroy(p->graph_exec);
+    if (p->graph)
+        cudaGraphDestroy(p->graph);
+    if (p->ev0)
+        cudaEventDestroy(p->ev0);
+    if (p->ev1)
+        cudaEventDestroy(p->ev1);
+    if (p->stream)
+        cudaStreamDestroy(p->stream);
+    if (p->h_list)
+        cudaFreeHost(p->h_list);
+    if (p->arena)
+        cudaFree(p->arena);
+    delete p;
+    return 0;
+}
+
+int jb_plan_stats(const jb_plan *p, jb_plan_stats_t *stats)
+{
+    JB_REQUIRE(p && stats, "plan: null argument");
+    *stats = p->stats;
+    return 0;
+}
+
+int jb_plan_upload(jb_plan *p, const void *const *h_data)
+{
+    JB_REQUIRE(p && h_data, "plan: null argument");
+    JB_CUDA(cudaSetDevice(p->device));
+    for (int i = 0; i < p->num_leaves; i++) {
+        const Node &n = p->nodes[i];
+        // raw (unsliced) element count
+        size_t raw_elems = n.elems;
+        if (n.slice_dep) {
+            for (const auto &sd : p->slice_descs)
+                if (static_cast<size_t>(sd.dst_off) * p->eb == n.offset) {
+                    for (int s = 0; s < sd.n_sl; s++)
+                        raw_elems *= sd.sl_dim[s];
+                }
+        }
+        JB_REQUIRE(h_data[i] != nullptr, "plan: null leaf data");
+        JB_CUDA(cudaMemcpyAsync(p->arena + n.raw_offset, h_data[i], raw_elems * p->eb,
+                                cudaMemcpyHostToDevice, p->stream));
+    }
+    p->shared_done = false;
+    return 0;
+}
+
+int jb_plan_reset(jb_plan *p)
+{
+    JB_REQUIRE(p, "plan: null argument");
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_CUDA(cudaMemsetAsync(p->arena + p->acc_off, 0, sizeof(double2) * p->result_elems, p->stream));
+    SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), 0, -1, 1);
+    JB_CUDA(cudaGetLastError());
+    return RunShared(p);
+}
+
+int jb_plan_run(jb_plan *p, int64_t first_slice, int64_t count)
+{
+    JB_REQUIRE(p, "plan: null argument");
+    JB_REQUIRE(first_slice >= 0 && count >= 0 && first_slice + count <= p->num_slices,
+               "plan: slice range out of bounds");
+    return RunSlices(p, first_slice, -1, count);
+}
+
+int jb_plan_run_list(jb_plan *p, const int64_t *ids, int64_t count)
+{
+    JB_REQUIRE(p && (ids || count == 0), "plan: null argument");
+    JB_REQUIRE(count <= p->list_cap, "plan: slice list longer than the number of slices");
+    for (int64_t i = 0; i < count; i++)
+        JB_REQUIRE(ids[i] >= 0 && ids[i] < p->num_slices, "plan: slice id out of bounds");
+    JB_CUDA(cudaSetDevice(p->device));
+    // the pinned staging buffer may still be in flight from an earlier call
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    for (int64_t i = 0; i < count; i++)
+        p->h_list[i] = ids[i];
+    if (count > 0)
+        JB_CUDA(cudaMemcpyAsync(p->arena + p->list_off, p->h_list, sizeof(long long) * count,
+                                cudaMemcpyHostToDevice, p->stream));
+    return RunSlices(p, 0, 0, count);
+}
+
+int jb_plan_sync(jb_plan *p)
+{
+    JB_REQUIRE(p, "plan: null argument");
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int jb_plan_result(jb_plan *p, double *h_out)
+{
+    JB_REQUIRE(p && h_out, "plan: null argument");
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_CUDA(cudaMemcpyAsync(h_out, p->arena + p->acc_off, sizeof(double2) * p->result_elems,
+                            cudaMemcpyDeviceToHost, p->stream));
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int jb_plan_slice_result(jb_plan *p, int64_t ordinal, void *h_out)
+{
+    JB_REQUIRE(p && h_out, "plan: null argument");
+    JB_REQUIRE(p->store_cap > 0, "plan: created without JB_PLAN_STORE_RESULTS");
+    JB_REQUIRE(ordinal >= 0 && ordinal < p->store_cap, "plan: slice ordinal out of range");
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_CUDA(cudaMemcpyAsync(h_out, p->arena + p->store_off + p->eb * p->result_elems * ordinal,
+                            p->eb * p->result_elems, cudaMemcpyDeviceToHost, p->stream));
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int jb_plan_node(jb_plan *p, int32_t node, void *h_out, int64_t *elems)
+{
+    JB_REQUIRE(p, "plan: null argument");
+    JB_REQUIRE(node >= 0 && node < static_cast<int>(p->nodes.size()), "plan: node out of range");
+    JB_REQUIRE((p->flags & JB_PLAN_KEEP_INTERMEDIATES) || node == p->result_node ||
+                   p->nodes[node].is_leaf,
+               "plan: created without JB_PLAN_KEEP_INTERMEDIATES");
+    const Node &n = p->nodes[node];
+    if (elems)
+        *elems = n.elems;
+    if (h_out) {
+        JB_CUDA(cudaSetDevice(p->device));
+        JB_CUDA(cudaMemcpyAsync(h_out, p->arena + n.offset, p->eb * n.elems, cudaMemcpyDeviceToHost,
+                                p->stream));
+        JB_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    return 0;
+}
+
+int jb_plan_last_ms(jb_plan *p, float *ms)
+{
+    JB_REQUIRE(p && ms, "plan: null argument");
+    JB_REQUIRE(p->have_run, "plan: nothing has been run yet");
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_CUDA(cudaEventSynchronize(p->ev1));
+    JB_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return 0;
+}
+
+int jb_plan_stream(jb_plan *p, void **stream)
+{
+    JB_REQUIRE(p && stream, "plan: null argument");
+    *stream = p->stream;
+    return 0;
+}
+
+int jb_plan_steps(const jb_plan *p, jb_step_info_t *steps, int32_t cap, int32_t *count)
+{
+    JB_REQUIRE(p && count, "plan: null argument");
+    *count = static_cast<int32_t>(p->steps.size());
+    for (int32_t i = 0; i < std::min<int32_t>(cap, *count); i++) {
+        const Step &st = p->steps[i];
+        jb_step_info_t &o = steps[i];
+        o.node_a = st.a;
+        o.node_b = st.b;
+        o.node_c = st.c;
+        o.shared = st.shared ? 1 : 0;
+        o.kernel = st.cp.kernel;
+        o.m = st.cp.m;
+        o.n = st.cp.n;
+        o.k = st.cp.k;
+        o.flops = st.cp.flops();
+        o.bytes = st.cp.bytes();
+    }
+    return 0;
+}
+
+int jb_plan_profile(jb_plan *p, int64_t slice, int reps, float *ms, int32_t cap)
+{
+    JB_REQUIRE(p && ms, "plan: null argument");
+    JB_REQUIRE(slice >= 0 && slice < p->num_slices, "plan: slice id out of bounds");
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_TRY(RunShared(p));
+    for (int32_t i = 0; i < cap; i++)
+        ms[i] = 0.f;
+    // one eager pass leaves every per-slice input in place (lifetimes are respected because the
+    // steps are replayed in plan order)
+    std::vector<cudaEvent_t> ev(p->slice_order.size() + 1);
+    for (auto &e : ev)
+        JB_CUDA(cudaEventCreate(&e));
+    std::vector<double> total(p->slice_order.size(), 0.0);
+    for (int r = 0; r < reps + 1; r++) {
+        SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), slice, -1, 0);
+        if (!p->slice_descs.empty()) {
+            const int n = static_cast<int>(p->slice_descs.size());
+            if (p->dtype == JB_C64)
+                SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(
+                    p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off),
+                    p->At<DeviceState>(p->state_off), p->At<long long>(p->list_off));
+            else
+                SliceLeavesKernel<uint4><<<n, 128, 0, p->stream>>>(
+                    p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off),
+                    p->At<DeviceState>(p->state_off), p->At<long long>(p->list_off));
+        }
+        for (size_t i = 0; i < p->slice_order.size(); i++) {
+            const Step &st = p->steps[p->slice_order[i]];
+            JB_CUDA(cudaEventRecord(ev[i], p->stream));
+            JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset,
+                                  p->arena + p->nodes[st.b].offset, p->arena + p->nodes[st.c].offset,
+                                  p->arena + p->ws_off, p->stream));
+        }
+        JB_CUDA(cudaEventRecord(ev.back(), p->stream));
+        JB_CUDA(cudaStreamSynchronize(p->stream));
+        if (r == 0)
+            continue; // warm-up
+        for (size_t i = 0; i < p->slice_order.size(); i++) {
+            float t = 0.f;
+            JB_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            total[i] += t;
+        }
+    }
+    for (size_t i = 0; i < p->slice_order.size(); i++) {
+        const int s = p->slice_order[i];
+        if (s < cap)
+            ms[s] = static_cast<float>(total[i] / std::max(reps, 1));
+    }
+    for (auto &e : ev)
+        cudaEventDestroy(e);
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,222 @@
+"""Network files and contraction plans (host side, Python).
+
+``NetworkFile`` reads/writes the reference's JSON tensor-network format
+(``TensorNetworkSerializer``, reference include/jet/TensorNetworkIO.hpp:94-187).
+``ContractionPlan`` owns a ``jb_plan`` (include/jetb200.h): the whole sliced network resident on
+one GPU, replacing per-slice ``TensorNetwork::SliceIndices`` copies + ``TaskBasedContractor`` tasks
+(reference include/jet/TensorNetwork.hpp:210-284, include/jet/TaskBasedContractor.hpp:162-322).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import (JB_PLAN_KEEP_INTERMEDIATES, JB_PLAN_NO_GRAPH, JB_PLAN_STORE_RESULTS, NetworkDesc, PlanStats,
+                   StepInfo, check, lib)
+from .ops import dtype_code
+
+
+class NetworkFile:
+    """Leaves (tags, indices, array) + optional path, as stored in the reference's JSON files."""
+
+    def __init__(self, tensors: List[Tuple[List[str], np.ndarray]], path: Sequence[Sequence[int]] = (),
+                 tags: Optional[List[List[str]]] = None):
+        self.tensors = [(list(idx), np.ascontiguousarray(arr)) for idx, arr in tensors]
+        self.path = [(int(a), int(b)) for a, b in path]
+        self.tags = tags if tags is not None else [[] for _ in tensors]
+
+    @classmethod
+    def loads(cls, text: str, dtype=np.complex64) -> "NetworkFile":
+        try:
+            js = json.loads(text)
+        except json.JSONDecodeError as e:
+            raise ValueError(f"Error parsing tensor network file: {e}") from e
+        if not isinstance(js, dict):
+            raise ValueError("Error parsing tensor network file: root element must be an object.")
+        if "tensors" not in js:
+            raise ValueError("Error parsing tensor network file: root object must contain 'tensors' key.")
+        tensors, tags = [], []
+        for i, entry in enumerate(js["tensors"]):
+            if len(entry) != 4:
+                raise ValueError(f"Error parsing tensor network file: tensor {i} must have 4 fields.")
+            tg, idx, shape, data = entry
+            flat = np.asarray(data, dtype=np.float64)
+            if flat.size and (flat.ndim != 2 or flat.shape[1] != 2):
+                raise ValueError(f"Error parsing tensor network file: invalid complex data in tensor {i}.")
+            arr = (flat[:, 0] + 1j * flat[:, 1]).astype(dtype) if flat.size else np.zeros(0, dtype)
+            if int(np.prod(shape, dtype=np.int64)) != arr.size:
+                raise ValueError(f"Error parsing tensor network file: tensor {i} has inconsistent shape.")
+            tensors.append((list(idx), arr.reshape([int(s) for s in shape])))
+            tags.append(list(tg))
+        return cls(tensors, js.get("path", []), tags)
+
+    @classmethod
+    def load(cls, filename: str, dtype=np.complex64) -> "NetworkFile":
+        with open(filename) as f:
+            return cls.loads(f.read(), dtype)
+
+    def dumps(self, indent=None) -> str:
+        out: Dict[str, list] = {}
+        if self.path:
+            out["path"] = [list(p) for p in self.path]
+        out["tensors"] = [
+            [list(tg), list(idx), [int(s) for s in arr.shape],
+             [[float(z.real), float(z.imag)] for z in arr.reshape(-1)]]
+            for (idx, arr), tg in zip(self.tensors, self.tags)
+        ]
+        return json.dumps(out, indent=indent, separators=(",", ":") if indent is None else None)
+
+    @property
+    def dtype(self):
+        return self.tensors[0][1].dtype
+
+    def index_dims(self) -> Dict[str, int]:
+        dims: Dict[str, int] = {}
+        for idx, arr in self.tensors:
+            for i, s in zip(idx, arr.shape):
+                dims[i] = int(s)
+        return dims
+
+
+class ContractionPlan:
+    """A sliced network + path resident on one GPU (wraps jb_plan)."""
+
+    def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), device: int = 0, keep_intermediates=False,
+                 use_graph=True, store_results=False, path: Optional[Sequence[Sequence[int]]] = None):
+        self.net = net
+        self.sliced = list(sliced)
+        self.device = device
+        self.dtype = np.dtype(net.dtype)
+        labels: Dict[str, int] = {}
+        for idx, _ in net.tensors:
+            for i in idx:
+                labels.setdefault(i, len(labels))
+        self.labels = labels
+        self.label_names = {v: k for k, v in labels.items()}
+        for s in self.sliced:
+            if s not in labels:
+                raise ValueError("Sliced index does not exist.")
+        ranks = [arr.ndim for _, arr in net.tensors]
+        extents = [int(s) for _, arr in net.tensors for s in arr.shape]
+        modes = [labels[i] for idx, _ in net.tensors for i in idx]
+        self._leaves = [np.ascontiguousarray(arr, dtype=self.dtype) for _, arr in net.tensors]
+        steps = [list(p) for p in (net.path if path is None else path)]
+        flat_path = [v for p in steps for v in p]
+        n = len(ranks)
+        self._rank = (C.c_int32 * max(n, 1))(*ranks)
+        self._extent = (C.c_int64 * max(len(extents), 1))(*extents)
+        self._mode = (C.c_int32 * max(len(modes), 1))(*modes)
+        self._data = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in self._leaves])
+        self._path = (C.c_int32 * max(len(flat_path), 1))(*flat_path)
+        self._sliced = (C.c_int32 * max(len(self.sliced), 1))(*[labels[s] for s in self.sliced])
+        flags = (JB_PLAN_KEEP_INTERMEDIATES if keep_intermediates else 0) | (0 if use_graph else JB_PLAN_NO_GRAPH) | (
+            JB_PLAN_STORE_RESULTS if store_results else 0)
+        desc = NetworkDesc(dtype_code(self.dtype), device, n, self._rank, self._extent, self._mode, self._data,
+                           len(steps), self._path, len(self.sliced), self._sliced, flags)
+        self._h = C.c_void_p()
+        check(lib().jb_plan_create(C.byref(desc), C.byref(self._h)))
+        st = PlanStats()
+        check(lib().jb_plan_stats(self._h, C.byref(st)))
+        self.stats = st
+        self.num_slices = int(st.num_slices)
+        self.result_elems = int(st.result_elems)
+        self.result_shape = [int(st.result_extent[i]) for i in range(st.result_rank)]
+        self.result_indices = [self.label_names[st.result_modes[i]] for i in range(st.result_rank)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().jb_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- execution ------------------------------------------------------------------------
+    def upload(self, leaves: Optional[Sequence[np.ndarray]] = None):
+        """(Re)copy leaf data host -> device; `leaves` may be pinned host buffers."""
+        if leaves is not None:
+            self._upload_ptrs = (C.c_void_p * len(leaves))(*[a.ctypes.data for a in leaves])
+            self._upload_keep = leaves
+            check(lib().jb_plan_upload(self._h, self._upload_ptrs))
+        else:
+            check(lib().jb_plan_upload(self._h, self._data))
+
+    def upload_ptrs(self, ptrs: Sequence[int]):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        check(lib().jb_plan_upload(self._h, arr))
+
+    def reset(self):
+        check(lib().jb_plan_reset(self._h))
+
+    def run(self, first: int = 0, count: Optional[int] = None):
+        count = self.num_slices - first if count is None else count
+        check(lib().jb_plan_run(self._h, first, count))
+
+    def run_list(self, ids: Sequence[int]):
+        arr = (C.c_int64 * max(len(ids), 1))(*[int(i) for i in ids])
+        check(lib().jb_plan_run_list(self._h, arr, len(ids)))
+
+    def sync(self):
+        check(lib().jb_plan_sync(self._h))
+
+    def result(self) -> np.ndarray:
+        """Sum over the slices run since reset(), complex128, shaped like the final tensor."""
+        out = np.empty(self.result_elems, dtype=np.complex128)
+        check(lib().jb_plan_result(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(self.result_shape)
+
+    def slice_result(self, ordinal: int) -> np.ndarray:
+        out = np.empty(self.result_elems, dtype=self.dtype)
+        check(lib().jb_plan_slice_result(self._h, ordinal, out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(self.result_shape)
+
+    def node(self, node: int) -> np.ndarray:
+        n = C.c_int64()
+        check(lib().jb_plan_node(self._h, node, None, C.byref(n)))
+        out = np.empty(n.value, dtype=self.dtype)
+        check(lib().jb_plan_node(self._h, node, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+
+    def last_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().jb_plan_last_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(lib().jb_plan_stream(self._h, C.byref(s)))
+        return int(s.value or 0)
+
+    def steps(self) -> List[StepInfo]:
+        n = C.c_int32()
+        check(lib().jb_plan_steps(self._h, None, 0, C.byref(n)))
+        arr = (StepInfo * max(n.value, 1))()
+        check(lib().jb_plan_steps(self._h, arr, n.value, C.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def profile(self, slice_id: int = 0, reps: int = 3) -> np.ndarray:
+        n = len(self.steps())
+        ms = np.zeros(max(n, 1), dtype=np.float32)
+        check(lib().jb_plan_profile(self._h, slice_id, reps, ms.ctypes.data_as(C.c_void_p), n))
+        return ms[:n]
+
+    def amplitude(self, slice_ids: Optional[Sequence[int]] = None) -> np.ndarray:
+        """reset + run (all slices, or the listed ones) + result."""
+        self.reset()
+        if slice_ids is None:
+            self.run(0, self.num_slices)
+        else:
+            self.run_list(list(slice_ids))
+        return self.result()

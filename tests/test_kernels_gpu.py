@@ -1,0 +1,224 @@
+"""GPU parity tests for K1 (permute), K2 (gemm) and the fused contraction, through the C ABI.
+
+Bar: permutation bit-exact; contraction within 1e-5 (complex64) / 1e-12 (complex128) relative of
+the oracle (normwise), the tolerance BASELINE.json's north_star states.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jet_oracle as jo
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {np.dtype(np.complex64): 1e-5, np.dtype(np.complex128): 1e-12}
+
+
+def rand_c(rng, n, dtype):
+    real = np.float32 if dtype == np.complex64 else np.float64
+    return (rng.uniform(-1, 1, n).astype(real) + 1j * rng.uniform(-1, 1, n).astype(real)).astype(dtype)
+
+
+def rel_err(x, ref):
+    x = np.asarray(x, dtype=np.complex128).reshape(-1)
+    ref = np.asarray(ref, dtype=np.complex128).reshape(-1)
+    return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from jet_b200 import ops as o
+    return o
+
+
+# ---------------------------------------------------------------- K1
+def test_permute_reference_fixtures_bit_exact(ops):
+    z = np.load(os.path.join(GOLDEN, "permute_cases.npz"))
+    bad = []
+    for i in range(int(z["count"])):
+        out = ops.permute(z[f"c{i}_in"], z[f"c{i}_shape"].tolist(), z[f"c{i}_perm"].tolist())
+        if not np.array_equal(out, z[f"c{i}_out"]):
+            bad.append((i, z[f"c{i}_shape"].tolist(), z[f"c{i}_perm"].tolist(), str(out.dtype)))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_permute_random_bit_permutations_vs_oracle(ops, dtype):
+    rng = np.random.default_rng(11)
+    bad = []
+    for r in list(range(1, 21)) + [22, 23]:
+        for trial in range(3 if r <= 16 else 1):
+            perm = rng.permutation(r).tolist()
+            x = rand_c(rng, 2 ** r, dtype)
+            out = ops.permute(x, [2] * r, perm)
+            if not np.array_equal(out, jo.transpose(x, [2] * r, perm)):
+                bad.append((r, perm))
+    assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_permute_pattern_classes(ops, dtype):
+    """P1..P5 of SURVEY §8(d): pull-to-back, pull-to-front, random, reversal, last-5-fixed."""
+    rng = np.random.default_rng(5)
+    r = 20
+    x = rand_c(rng, 2 ** r, dtype)
+    pull = sorted(rng.choice(r, 3, replace=False).tolist())
+    rest = [i for i in range(r) if i not in pull]
+    perms = [rest + pull, pull + rest, rng.permutation(r).tolist(), list(range(r))[::-1],
+             rng.permutation(r - 5).tolist() + list(range(r - 5, r)), list(range(r)),
+             [1, 0] + list(range(2, r)), list(range(r - 2)) + [r - 1, r - 2]]
+    for perm in perms:
+        assert np.array_equal(ops.permute(x, [2] * r, perm), jo.transpose(x, [2] * r, perm)), perm
+
+
+def test_permute_mixed_and_non_pow2_shapes(ops):
+    rng = np.random.default_rng(6)
+    for shape in ([4, 16, 2, 8, 4], [64, 64], [30, 50, 70], [3, 5, 7, 2, 4], [1, 8, 1, 4], [7], [2, 3], [6, 1, 5]):
+        for dtype in (np.complex64, np.complex128):
+            perm = rng.permutation(len(shape)).tolist()
+            x = rand_c(rng, int(np.prod(shape)), dtype)
+            assert np.array_equal(ops.permute(x, shape, perm), jo.transpose(x, shape, perm)), (shape, perm)
+
+
+def test_permute_large_roundtrip_property(ops):
+    """Full-size property (2^26 complex64 = 512 MiB): permute then inverse permute is the identity,
+    and a permutation preserves the multiset (checksum)."""
+    r = 26
+    rng = np.random.default_rng(9)
+    x = (np.arange(2 ** r, dtype=np.float32) % 8191).astype(np.float32)
+    x = (x + 1j * (x + 1)).astype(np.complex64)
+    perm = rng.permutation(r).tolist()
+    inv = np.argsort(perm).tolist()
+    y = ops.permute(x, [2] * r, perm)
+    assert y.view(np.float32).astype(np.float64).sum() == x.view(np.float32).astype(np.float64).sum()
+    # spot-check against the definition on a sample of addresses
+    idx = rng.integers(0, 2 ** r, 2000)
+    bits = (idx[:, None] >> np.arange(r - 1, -1, -1)[None, :]) & 1  # out multi-index, axis 0 first
+    src = np.zeros(len(idx), dtype=np.int64)
+    for j in range(r):
+        src |= bits[:, j].astype(np.int64) << (r - 1 - perm[j])
+    assert np.array_equal(y[idx], x[src])
+    z = ops.permute(y, [2] * r, inv)
+    assert np.array_equal(z, x)
+
+
+def test_permute_rejects_bad_arguments(ops):
+    from jet_b200 import JetB200Error
+    x = np.zeros(8, np.complex64)
+    with pytest.raises(JetB200Error):
+        ops.permute(x, [2, 2, 2], [0, 0, 1])
+    with pytest.raises(ValueError):
+        ops.permute(x, [2, 2], [0, 1])
+
+
+# ---------------------------------------------------------------- K2
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_gemm_shapes_vs_oracle(ops, dtype):
+    rng = np.random.default_rng(3)
+    shapes = [(1, 1, 1), (1, 1, 1000), (1, 7, 33), (9, 1, 130), (2, 2, 12), (64, 64, 64), (65, 63, 17), (128, 256, 96),
+              (16, 32, 1 << 15), (1, 1, 1 << 18), (300, 5, 4096), (5, 300, 2500), (1000, 3, 2), (3, 1000, 1)]
+    for m, n, k in shapes:
+        a = rand_c(rng, m * k, dtype).reshape(m, k)
+        b = rand_c(rng, k * n, dtype).reshape(k, n)
+        c = ops.gemm(a, b)
+        ref = a.astype(np.complex128) @ b.astype(np.complex128)
+        assert rel_err(c, ref) < TOL[np.dtype(dtype)], (m, n, k, rel_err(c, ref))
+
+
+def test_gemm_kat_from_reference(ops):
+    # test/Test_Tensor.cpp:372-397: 2x12 . 12x2 of (0.5, 0.25) -> (2.25, 3.0)
+    a = np.full((2, 12), 0.5 + 0.25j, dtype=np.complex64)
+    b = np.full((12, 2), 0.5 + 0.25j, dtype=np.complex64)
+    assert np.array_equal(ops.gemm(a, b), np.full((2, 2), 2.25 + 3.0j, dtype=np.complex64))
+
+
+# ---------------------------------------------------------------- fused contraction
+def test_contract_reference_fixtures(ops):
+    z = np.load(os.path.join(GOLDEN, "contract_cases.npz"))
+    bad = []
+    for i in range(int(z["count"])):
+        sa, sb = z[f"c{i}_sa"].tolist(), z[f"c{i}_sb"].tolist()
+        a = z[f"c{i}_a"].reshape(sa)
+        b = z[f"c{i}_b"].reshape(sb)
+        c, _ = ops.contract(a, z[f"c{i}_ia"].tolist(), b, z[f"c{i}_ib"].tolist())
+        e = rel_err(c, z[f"c{i}_c"])
+        if not e < TOL[a.dtype]:
+            bad.append((i, sa, z[f"c{i}_ia"].tolist(), sb, z[f"c{i}_ib"].tolist(), str(a.dtype), e))
+    assert not bad, bad[:6]
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_contract_random_tn_shapes_vs_oracle(ops, dtype):
+    """S1/S3-style shapes of SURVEY §8(d): big operand x small operand with scattered contracted
+    indices in both orders, both-large (TTGT), split-K."""
+    rng = np.random.default_rng(17)
+    bad = []
+    specs = []
+    for ra in (5, 9, 14, 18, 20):
+        for rb in (2, 3, 4, 6, 8):
+            for c in range(0, min(ra, rb) + 1):
+                if rb - c > 6 or (rng.random() < 0.5 and ra > 9):
+                    continue
+                specs.append((ra, rb, c))
+    specs += [(13, 13, 5), (14, 14, 10), (16, 15, 13), (18, 18, 16), (12, 12, 12), (20, 20, 20)]
+    for ra, rb, c in specs:
+        for swap in (False, True):
+            ids_a = list(range(ra))
+            common = sorted(rng.choice(ra, c, replace=False).tolist())
+            ids_b = common + list(range(100, 100 + rb - c))
+            ids_b = [ids_b[i] for i in rng.permutation(rb)]
+            a = rand_c(rng, 2 ** ra, dtype).reshape([2] * ra)
+            b = rand_c(rng, 2 ** rb, dtype).reshape([2] * rb)
+            if swap:
+                a, b, ids_a, ids_b = b, a, ids_b, ids_a
+            out, modes = ops.contract(a, ids_a, b, ids_b)
+            idx, ref = jo.contract(([str(i) for i in ids_a], a), ([str(i) for i in ids_b], b))
+            if [str(m) for m in modes] != idx:
+                bad.append(("modes", ra, rb, c, swap))
+                continue
+            e = rel_err(out, ref)
+            if not e < TOL[np.dtype(dtype)]:
+                bad.append((ra, rb, c, swap, e))
+    assert not bad, bad[:8]
+
+
+def test_contract_dim4_and_non_pow2(ops):
+    rng = np.random.default_rng(23)
+    cases = [([4] * 7, list(range(7)), [4] * 3, [2, 50, 5]), ([4] * 6, list(range(6)), [4] * 6, [9, 3, 8, 1, 7, 0]),
+             ([3, 5, 7], [0, 1, 2], [7, 3, 2], [2, 0, 9]), ([6, 10], [0, 1], [10, 6], [1, 0]),
+             ([2, 3, 5], [0, 1, 2], [5, 3, 4], [2, 1, 3])]
+    for sa, ia, sb, ib in cases:
+        for dtype in (np.complex64, np.complex128):
+            a = rand_c(rng, int(np.prod(sa)), dtype).reshape(sa)
+            b = rand_c(rng, int(np.prod(sb)), dtype).reshape(sb)
+            out, _ = ops.contract(a, ia, b, ib)
+            _, ref = jo.contract(([str(i) for i in ia], a), ([str(i) for i in ib], b))
+            assert out.shape == ref.shape
+            assert rel_err(out, ref) < TOL[np.dtype(dtype)], (sa, ia, sb, ib)
+
+
+def test_contract_linearity_property_large(ops):
+    """Size-independent property at 2^24 elements: contract(a1 + a2, b) == contract(a1, b) +
+    contract(a2, b) up to rounding, and exact small-integer data gives exact results."""
+    r = 24
+    rng = np.random.default_rng(31)
+    ids_a = list(range(r))
+    ids_b = [3, 100, 17, 101, 23]
+    a = (rng.integers(-2, 3, 2 ** r) + 1j * rng.integers(-2, 3, 2 ** r)).astype(np.complex64).reshape([2] * r)
+    b = (rng.integers(-2, 3, 32) + 1j * rng.integers(-2, 3, 32)).astype(np.complex64).reshape([2] * 5)
+    out, _ = ops.contract(a, ids_a, b, ids_b)
+    _, ref = jo.contract(([str(i) for i in ids_a], a), ([str(i) for i in ids_b], b))
+    assert np.array_equal(out, ref)  # integers: exact in fp32 irrespective of summation order
+
+
+def test_add_and_slice(ops):
+    rng = np.random.default_rng(2)
+    for dtype in (np.complex64, np.complex128):
+        a = rand_c(rng, 3000, dtype)
+        b = rand_c(rng, 3000, dtype)
+        assert np.array_equal(ops.add(a, b), a + b)
+        t = rand_c(rng, 2 * 3 * 4 * 5, dtype).reshape(2, 3, 4, 5)
+        for ax in range(4):
+            assert np.array_equal(ops.slice_index(t, ax, 1), np.take(t, 1, axis=ax))

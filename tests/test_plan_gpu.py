@@ -1,0 +1,174 @@
+"""GPU parity tests for the contraction plan (whole sliced network on the device) against the
+oracle and the golden amplitudes produced by the unmodified reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jet_oracle as jo
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+M10_SLICED = "p7 s7 h4 m1 m2 I2 V4 z2 t4 C1".split()
+M12_SLICED = "h5 m H10 w y J S G10 P0".split()
+
+
+def gold():
+    return json.load(open(os.path.join(GOLDEN, "amplitudes.json")))
+
+
+def rel(x, ref):
+    return abs(complex(x) - complex(ref)) / abs(complex(ref))
+
+
+def small_network(dtype, rng, dims=2):
+    """A closed 8-tensor network with a fixed path (hand-made; exercises all plan features)."""
+    real = np.float32 if dtype == np.complex64 else np.float64
+    edges = {"a": (0, 1), "b": (1, 2), "c": (2, 3), "d": (3, 0), "e": (0, 4), "f": (1, 5), "g": (2, 6), "h": (3, 7),
+             "i": (4, 5), "j": (5, 6), "k": (6, 7), "l": (7, 4)}
+    tensors = []
+    for t in range(8):
+        idx = [e for e, (u, v) in edges.items() if t in (u, v)]
+        n = dims ** len(idx)
+        arr = (rng.uniform(-1, 1, n).astype(real) + 1j * rng.uniform(-1, 1, n).astype(real)).astype(dtype)
+        tensors.append((idx, arr.reshape([dims] * len(idx))))
+    path = [(0, 1), (2, 3), (4, 5), (6, 7), (8, 9), (10, 11), (12, 13)]
+    return tensors, path
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+@pytest.mark.parametrize("dims", [2, 4, 3])
+def test_small_network_sliced_vs_oracle(dtype, dims):
+    from jet_b200 import ContractionPlan, NetworkFile
+    rng = np.random.default_rng(dims)
+    tensors, path = small_network(dtype, rng, dims)
+    onet = jo.Network(tensors, path)
+    tol = 1e-5 if dtype == np.complex64 else 1e-12
+    for sliced in ([], ["a"], ["c", "j"], ["l", "a", "g"]):
+        ref = jo.amplitude(onet, sliced).reshape(-1)[0]
+        for graph in (True, False):
+            with ContractionPlan(NetworkFile(tensors, path), sliced, use_graph=graph, store_results=True) as plan:
+                assert plan.num_slices == dims ** len(sliced)
+                got = plan.amplitude().reshape(-1)[0]
+                assert rel(got, ref) < tol, (sliced, graph)
+                # per-slice results in slice order
+                for v in range(plan.num_slices):
+                    r = jo.amplitude(onet, sliced, [v]).reshape(-1)[0]
+                    assert rel(plan.slice_result(v).reshape(-1)[0], r) < 10 * tol
+                # explicit slice list, reversed order
+                if sliced:
+                    ids = list(range(plan.num_slices))[::-1]
+                    assert rel(plan.amplitude(ids).reshape(-1)[0], ref) < tol
+
+
+def test_open_network_result_tensor_and_intermediates():
+    """Open output indices: the result is a tensor, reduced elementwise over slices
+    (test/Test_TaskBasedContractor.cpp:473-491); KEEP_INTERMEDIATES exposes every step."""
+    from jet_b200 import ContractionPlan, NetworkFile
+    rng = np.random.default_rng(4)
+    tensors, path = small_network(np.complex64, rng, 2)
+    tensors[0] = (tensors[0][0] + ["out0"], np.stack([tensors[0][1], 2 * tensors[0][1]], axis=-1))
+    tensors[6] = (["out1"] + tensors[6][0], np.stack([tensors[6][1], -tensors[6][1], 1j * tensors[6][1]], axis=0))
+    onet = jo.Network(tensors, path)
+    nodes = onet.contract(keep_steps=True)
+    with ContractionPlan(NetworkFile(tensors, path), [], keep_intermediates=True) as plan:
+        got = plan.amplitude()
+        assert plan.result_indices == nodes[-1][0]
+        assert np.linalg.norm(got - nodes[-1][1]) / np.linalg.norm(nodes[-1][1]) < 1e-5
+        for n in range(len(tensors), len(nodes)):
+            x = plan.node(n)
+            ref = nodes[n][1].reshape(-1)
+            assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-5, n
+    sliced = ["b", "k"]
+    ref = jo.amplitude(onet, sliced)
+    with ContractionPlan(NetworkFile(tensors, path), sliced) as plan:
+        got = plan.amplitude()
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5
+
+
+def test_plan_errors():
+    from jet_b200 import ContractionPlan, JetB200Error, NetworkFile
+    rng = np.random.default_rng(1)
+    tensors, path = small_network(np.complex64, rng)
+    with pytest.raises(ValueError, match="Sliced index does not exist."):
+        ContractionPlan(NetworkFile(tensors, path), ["nope"])
+    with pytest.raises(JetB200Error, match="Node ID 2 in contraction pair is invalid."):
+        ContractionPlan(NetworkFile(tensors, [(0, 99)]))
+
+
+@pytest.mark.parametrize("dt", ["complex64", "complex128"])
+def test_m10_sliced_matches_reference_goldens(data_dir, dt):
+    from jet_b200 import ContractionPlan, NetworkFile
+    g = gold()
+    net = NetworkFile.load(os.path.join(data_dir, "m10.json"), np.dtype(dt))
+    tol = 1e-5 if dt == "complex64" else 1e-12
+    with ContractionPlan(net, M10_SLICED[:6], store_results=True) as plan:
+        assert plan.num_slices == 64
+        assert plan.stats.jet_flops_per_slice == g[f"m10_s6_slice0_{dt}"]["jet_flops"]
+        total = plan.amplitude().reshape(-1)[0]
+        for v in range(4):
+            e = g[f"m10_s6_slice{v}_{dt}"]
+            assert rel(plan.slice_result(v).reshape(-1)[0], complex(e["re"], e["im"])) < tol, v
+        e = g[f"m10_s6_sum64_{dt}"]
+        assert rel(total, complex(e["re"], e["im"])) < tol
+        # complex64 result also within tolerance of the complex128 reference
+        e = g["m10_s6_sum64_complex128"]
+        assert rel(total, complex(e["re"], e["im"])) < 1e-5
+    with ContractionPlan(net, M10_SLICED[:10]) as plan:
+        assert plan.num_slices == 1024
+        plan.reset()
+        plan.run(0, 16)
+        e = g[f"m10_s10_sum_first16_{dt}"]
+        assert rel(plan.result().reshape(-1)[0], complex(e["re"], e["im"])) < tol
+
+
+def test_m10_unsliced_full_amplitude(data_dir):
+    from jet_b200 import ContractionPlan, NetworkFile
+    g = gold()
+    net = NetworkFile.load(os.path.join(data_dir, "m10.json"), np.complex64)
+    with ContractionPlan(net, []) as plan:
+        got = plan.amplitude().reshape(-1)[0]
+    e = g["m10_s6_sum64_complex128"]  # the full amplitude equals the sum over all slices
+    assert rel(got, complex(e["re"], e["im"])) < 1e-5
+    if "m10_full_complex64" in g:
+        e = g["m10_full_complex64"]
+        assert rel(got, complex(e["re"], e["im"])) < 1e-5
+
+
+@pytest.mark.parametrize("tot", [0, 10, 30, 60])
+def test_gbs_fock4_c128_matches_reference_goldens(data_dir, tot):
+    from jet_b200 import ContractionPlan, NetworkFile
+    g = gold()
+    fn = os.path.join(data_dir, f"gbs_dim2_nc1_lw8_rp5_fock4_total{tot}_0.kraken.json")
+    for dt, tol in (("complex128", 1e-12), ("complex64", 1e-5)):
+        net = NetworkFile.load(fn, np.dtype(dt))
+        with ContractionPlan(net, []) as plan:
+            got = plan.amplitude().reshape(-1)[0]
+        e = g[f"gbs_fock4_total{tot}_{dt}"]
+        assert rel(got, complex(e["re"], e["im"])) < tol, (tot, dt)
+    # sliced over two dim-4 indices: 16 slices must sum to the same amplitude
+    net = NetworkFile.load(fn, np.complex128)
+    dims = net.index_dims()
+    sliced = sorted(dims)[:2]
+    with ContractionPlan(net, sliced) as plan:
+        assert plan.num_slices == 16
+        got = plan.amplitude().reshape(-1)[0]
+    e = g[f"gbs_fock4_total{tot}_complex128"]
+    assert rel(got, complex(e["re"], e["im"])) < 1e-11
+
+
+def test_m12_single_slices_match_reference_goldens(data_dir):
+    from jet_b200 import ContractionPlan, NetworkFile
+    g = gold()
+    if "m12_s9_slice0_complex64" not in g:
+        pytest.skip("heavy goldens not generated")
+    net = NetworkFile.load(os.path.join(data_dir, "m12.json"), np.complex64)
+    with ContractionPlan(net, M12_SLICED, store_results=True) as plan:
+        assert plan.num_slices == 512
+        plan.reset()
+        plan.run(0, 2)
+        for v in (0, 1):
+            e = g[f"m12_s9_slice{v}_complex64"]
+            assert rel(plan.slice_result(v).reshape(-1)[0], complex(e["re"], e["im"])) < 1e-5, v
