@@ -468,12 +468,25 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             p->nodes[st.b].used_by_slice_step = true;
         }
     }
+    // fixed regions first (never recycled): workspace, accumulator, per-slice result store, state,
+    // slice-id list, slice descriptors
     size_t ws_max = 0;
+    for (const Step &st : p->steps)
+        ws_max = std::max(ws_max, st.cp.ws_bytes);
+    p->ws_bytes = ws_max;
+    p->ws_off = alloc.Alloc(std::max<size_t>(ws_max, 512));
+    p->acc_off = alloc.Alloc(sizeof(double2) * p->result_elems);
+    p->store_cap = (d->flags & JB_PLAN_STORE_RESULTS) ? p->num_slices : 0;
+    if (p->store_cap > 0)
+        p->store_off = alloc.Alloc(p->eb * p->result_elems * p->store_cap);
+    p->state_off = alloc.Alloc(sizeof(DeviceState));
+    p->list_cap = std::max<int64_t>(p->num_slices, 1);
+    p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
+    p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
     for (size_t e = 0; e < exec.size(); e++) {
         const Step &st = p->steps[exec[e]];
         Node &C = p->nodes[st.c];
         C.offset = alloc.Alloc(C.elems * p->eb);
-        ws_max = std::max(ws_max, st.cp.ws_bytes);
         if (keep)
             continue;
         for (int in : {st.a, st.b}) {
@@ -487,16 +500,6 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             alloc.Free(I.offset, I.elems * p->eb);
         }
     }
-    p->ws_bytes = ws_max;
-    p->ws_off = alloc.Alloc(std::max<size_t>(ws_max, 512));
-    p->acc_off = alloc.Alloc(sizeof(double2) * p->result_elems);
-    p->store_cap = (d->flags & JB_PLAN_STORE_RESULTS) ? p->num_slices : 0;
-    if (p->store_cap > 0)
-        p->store_off = alloc.Alloc(p->eb * p->result_elems * p->store_cap);
-    p->state_off = alloc.Alloc(sizeof(DeviceState));
-    p->list_cap = std::max<int64_t>(p->num_slices, 1);
-    p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
-    p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
     p->arena_bytes = alloc.Peak();
 
     // ---- device resources ---------------------------------------------------------------------------
