@@ -1,5 +1,6 @@
 // extern "C" entry points of libjetb200.so (see include/jetb200.h for the contract and the
 // reference interfaces each one replaces).
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -31,6 +32,22 @@ int NumSMs()
         sms[dev] = v;
     }
     return sms[dev];
+}
+
+int BlocksPerSM(const void *kernel, int threads, size_t dyn_smem)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, size_t>, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair(kernel, dyn_smem);
+    auto it = cache.find(key);
+    if (it != cache.end())
+        return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n < 1)
+        n = 1;
+    cache[key] = n;
+    return n;
 }
 
 namespace {

@@ -49,6 +49,14 @@ inline int Log2(int64_t x)
 
 int NumSMs();
 
+// Resident CTAs per SM of a kernel (cached per function pointer): persistent grids are sized as
+// NumSMs() * this so that every CTA of the grid is resident at once (no partial tail wave).
+int BlocksPerSM(const void *kernel, int threads, size_t dyn_smem);
+template <typename K> inline int PersistentBlocksPerSM(K kernel, int threads, size_t dyn_smem)
+{
+    return BlocksPerSM(reinterpret_cast<const void *>(kernel), threads, dyn_smem);
+}
+
 // ---- K1: permutation ---------------------------------------------------------------------------
 // Bit-permutation description: the tensor has n address bits (all extents powers of two);
 // output address bit j is input address bit src[j].

@@ -80,7 +80,7 @@ __device__ __forceinline__ unsigned long long InsertZeros(unsigned long long x, 
 
 // KC: k values held in registers at once; NR: outputs per thread per pass; XT: x values per thread
 template <typename R, int KC, int NR, int XT>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, (KC * XT * sizeof(R) <= 32 && NR <= 4) ? 4 : ((KC * NR * XT * sizeof(R) <= 256) ? 3 : 2))
     StreamContractKernel(const typename Cx<R>::type *__restrict__ S,
                          const typename Cx<R>::type *__restrict__ Rsd,
                          typename Cx<R>::type *__restrict__ out,
@@ -200,13 +200,15 @@ int LaunchStreamT(const StreamParams &p, const void *s, const void *r, void *out
     constexpr int XT = sizeof(R) == 4 ? 2 : 1;
     const long long tile = static_cast<long long>(kStreamThreads) * XT;
     const long long tiles = (p.x_count + tile - 1) / tile;
-    const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(NumSMs()) * 4));
     const size_t smem = sizeof(C) << (p.log_k + p.log_y);
     auto kernel = StreamContractKernel<R, KC, NR, XT>;
     if (smem > 48 * 1024) {
         JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
     }
+    const long long resident =
+        static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kStreamThreads, smem);
+    const int grid = static_cast<int>(std::min<long long>(tiles, resident));
     kernel<<<grid, kStreamThreads, smem, stream>>>(static_cast<const C *>(s),
                                                    static_cast<const C *>(r),
                                                    static_cast<C *>(out), p);

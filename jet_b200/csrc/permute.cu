@@ -27,7 +27,6 @@ namespace {
 
 constexpr int kPermThreads = 256;
 constexpr int kPermSmemBytes = 16384;
-constexpr int kPermCtasPerSm = 8;
 
 struct BitPermParams {
     int t;       // tile bits
@@ -235,24 +234,27 @@ int PlanBitPerm(int n, const uint8_t *src, int elem_bytes, BitPermParams *p)
 template <typename V, typename OffT>
 int LaunchBitsT(const void *in, void *out, const BitPermParams &p, cudaStream_t stream)
 {
-    const long long max_grid = static_cast<long long>(NumSMs()) * kPermCtasPerSm;
-    const int grid = static_cast<int>(std::min<long long>(p.n_tiles, max_grid));
     const int ept = std::max(1, (1 << p.t) / kPermThreads);
     const V *i = static_cast<const V *>(in);
     V *o = static_cast<V *>(out);
+    auto grid_for = [&](auto kernel) {
+        const long long resident =
+            static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kPermThreads, 0);
+        return static_cast<int>(std::min<long long>(p.n_tiles, resident));
+    };
     switch (ept) {
     case 1:
-        PermuteBitsKernel<V, 1, OffT><<<grid, kPermThreads, 0, stream>>>(i, o, p);
+        PermuteBitsKernel<V, 1, OffT><<<grid_for(PermuteBitsKernel<V, 1, OffT>), kPermThreads, 0, stream>>>(i, o, p);
         break;
     case 2:
-        PermuteBitsKernel<V, 2, OffT><<<grid, kPermThreads, 0, stream>>>(i, o, p);
+        PermuteBitsKernel<V, 2, OffT><<<grid_for(PermuteBitsKernel<V, 2, OffT>), kPermThreads, 0, stream>>>(i, o, p);
         break;
     case 4:
-        PermuteBitsKernel<V, 4, OffT><<<grid, kPermThreads, 0, stream>>>(i, o, p);
+        PermuteBitsKernel<V, 4, OffT><<<grid_for(PermuteBitsKernel<V, 4, OffT>), kPermThreads, 0, stream>>>(i, o, p);
         break;
     case 8:
         if constexpr (sizeof(V) == 8) {
-            PermuteBitsKernel<V, 8, OffT><<<grid, kPermThreads, 0, stream>>>(i, o, p);
+            PermuteBitsKernel<V, 8, OffT><<<grid_for(PermuteBitsKernel<V, 8, OffT>), kPermThreads, 0, stream>>>(i, o, p);
             break;
         }
         [[fallthrough]];
