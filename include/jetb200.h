@@ -120,6 +120,7 @@ int jb_gemm_host(int dtype, int64_t m, int64_t n, int64_t k, const void *h_a, co
 int jb_add_host(int dtype, int64_t n, const void *h_a, const void *h_b, void *h_c);
 int jb_slice_host(int dtype, const void *h_in, void *h_out, int rank, const int64_t *extent_in,
                   int axis, int64_t value);
+int jb_conj_host(int dtype, int64_t n, const void *h_in, void *h_out);
 
 /* ---- contraction plan: a whole (sliced) network + path on one GPU ----------------------------
  * Replaces the per-task execution of TaskBasedContractor (AddContractionTasks / AddReductionTask /

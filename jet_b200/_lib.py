@@ -97,7 +97,7 @@ SYMBOLS = [
     "jb_memcpy_d2d", "jb_memset_zero", "jb_stream_create", "jb_stream_destroy", "jb_stream_sync",
     "jb_permute", "jb_gemm_ws_bytes", "jb_gemm", "jb_contract_info", "jb_contract", "jb_add",
     "jb_slice", "jb_conj", "jb_permute_host", "jb_contract_host", "jb_gemm_host", "jb_add_host",
-    "jb_slice_host", "jb_plan_create", "jb_plan_destroy", "jb_plan_stats", "jb_plan_upload",
+    "jb_slice_host", "jb_conj_host", "jb_plan_create", "jb_plan_destroy", "jb_plan_stats", "jb_plan_upload",
     "jb_plan_reset", "jb_plan_run", "jb_plan_run_list", "jb_plan_result", "jb_plan_slice_result",
     "jb_plan_node", "jb_plan_sync", "jb_plan_last_ms", "jb_plan_stream", "jb_plan_steps",
     "jb_plan_profile",
@@ -141,6 +141,7 @@ def lib():
                                C.c_int64, C.c_void_p]
         L.jb_slice_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                     C.c_int64]
+        L.jb_conj_host.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.jb_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.jb_free.argtypes = [C.c_void_p]
         L.jb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]

@@ -52,17 +52,45 @@ int BlocksPerSM(const void *kernel, int threads, size_t dyn_smem)
 
 namespace {
 
-// RAII device buffer for the host-buffer entry points
+// Grow-only, per-thread device scratch for the host-buffer entry points: Jet::Tensor operators call
+// these many times on tiny tensors, so a cudaMalloc/cudaFree per call would dominate.
+struct ScratchSlot {
+    void *p = nullptr;
+    size_t cap = 0;
+    int device = -1;
+};
+struct ScratchPool {
+    ScratchSlot slot[4];
+    ~ScratchPool()
+    {
+        for (auto &s : slot)
+            if (s.p)
+                cudaFree(s.p); // best effort (the context may already be gone at exit)
+    }
+};
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf()
-    {
-        if (p)
-            cudaFree(p);
-    }
+    int index;
+    explicit DevBuf(int i) : index(i) {}
     int Alloc(size_t bytes)
     {
-        JB_CUDA(cudaMalloc(&p, bytes == 0 ? 1 : bytes));
+        thread_local ScratchPool pool;
+        ScratchSlot &s = pool.slot[index];
+        int dev = 0;
+        JB_CUDA(cudaGetDevice(&dev));
+        bytes = bytes == 0 ? 16 : bytes;
+        if (s.p == nullptr || s.cap < bytes || s.device != dev) {
+            if (s.p) {
+                cudaFree(s.p);
+                s.p = nullptr;
+                s.cap = 0;
+            }
+            const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+            JB_CUDA(cudaMalloc(&s.p, want));
+            s.cap = want;
+            s.device = dev;
+        }
+        p = s.p;
         return 0;
     }
 };
@@ -254,7 +282,7 @@ int jb_permute_host(int dtype, const void *h_in, void *h_out, int rank, const in
 {
     JB_REQUIRE(h_in && h_out, "permute: null buffer");
     const size_t bytes = ElemBytes(dtype) * static_cast<size_t>(Product(rank, extent_in));
-    DevBuf in, out;
+    DevBuf in(0), out(1);
     JB_TRY(in.Alloc(bytes));
     JB_TRY(out.Alloc(bytes));
     JB_CUDA(cudaMemcpy(in.p, h_in, bytes, cudaMemcpyHostToDevice));
@@ -273,7 +301,7 @@ int jb_contract_host(int dtype, int rank_a, const int64_t *extent_a, const int32
     const size_t eb = ElemBytes(dtype);
     const size_t ba = eb * static_cast<size_t>(P.m * P.k), bb = eb * static_cast<size_t>(P.k * P.n),
                  bc = eb * static_cast<size_t>(P.m * P.n);
-    DevBuf a, b, c, ws;
+    DevBuf a(0), b(1), c(2), ws(3);
     JB_TRY(a.Alloc(ba));
     JB_TRY(b.Alloc(bb));
     JB_TRY(c.Alloc(bc));
@@ -291,7 +319,7 @@ int jb_gemm_host(int dtype, int64_t m, int64_t n, int64_t k, const void *h_a, co
     JB_REQUIRE(h_a && h_b && h_c, "gemm: null buffer");
     JB_REQUIRE(m >= 1 && n >= 1 && k >= 1, "gemm: dimensions must be positive");
     const size_t eb = ElemBytes(dtype);
-    DevBuf a, b, c, ws;
+    DevBuf a(0), b(1), c(2), ws(3);
     const size_t wsb = GemmWorkspaceBytes(dtype, m, n, k);
     JB_TRY(a.Alloc(eb * m * k));
     JB_TRY(b.Alloc(eb * k * n));
@@ -308,7 +336,7 @@ int jb_add_host(int dtype, int64_t n, const void *h_a, const void *h_b, void *h_
 {
     JB_REQUIRE(h_a && h_b && h_c, "add: null buffer");
     const size_t bytes = ElemBytes(dtype) * static_cast<size_t>(n);
-    DevBuf a, b, c;
+    DevBuf a(0), b(1), c(2);
     JB_TRY(a.Alloc(bytes));
     JB_TRY(b.Alloc(bytes));
     JB_TRY(c.Alloc(bytes));
@@ -316,6 +344,19 @@ int jb_add_host(int dtype, int64_t n, const void *h_a, const void *h_b, void *h_
     JB_CUDA(cudaMemcpy(b.p, h_b, bytes, cudaMemcpyHostToDevice));
     JB_TRY(LaunchAdd(dtype, n, a.p, b.p, c.p, nullptr));
     JB_CUDA(cudaMemcpy(h_c, c.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int jb_conj_host(int dtype, int64_t n, const void *h_in, void *h_out)
+{
+    JB_REQUIRE(h_in && h_out, "conj: null buffer");
+    const size_t bytes = ElemBytes(dtype) * static_cast<size_t>(n);
+    DevBuf in(0), out(1);
+    JB_TRY(in.Alloc(bytes));
+    JB_TRY(out.Alloc(bytes));
+    JB_CUDA(cudaMemcpy(in.p, h_in, bytes, cudaMemcpyHostToDevice));
+    JB_TRY(LaunchConj(dtype, n, in.p, out.p, nullptr));
+    JB_CUDA(cudaMemcpy(h_out, out.p, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -327,7 +368,7 @@ int jb_slice_host(int dtype, const void *h_in, void *h_out, int rank, const int6
     const size_t eb = ElemBytes(dtype);
     const size_t n_in = static_cast<size_t>(Product(rank, extent_in));
     const size_t n_out = n_in / static_cast<size_t>(extent_in[axis]);
-    DevBuf in, out;
+    DevBuf in(0), out(1);
     JB_TRY(in.Alloc(eb * n_in));
     JB_TRY(out.Alloc(eb * n_out));
     JB_CUDA(cudaMemcpy(in.p, h_in, eb * n_in, cudaMemcpyHostToDevice));

@@ -1,0 +1,88 @@
+"""`jet`-compatible Python API: the names of the reference's ``jet`` package for the hot path
+(reference python/jet/__init__.py:6-21 and python/jet/factory.py:40-151), backed by the B200
+engine.  Usage::
+
+    from jet_b200 import jet
+    tn = jet.TensorNetwork(dtype=np.complex64)
+    tbc = jet.TaskBasedContractor(dtype=np.complex64)
+
+As in the reference the default ``dtype`` is complex128.  The circuit / gate / XIR front end of the
+reference package is out of scope.
+"""
+from typing import Union
+
+import numpy as np
+
+from .bindings import (  # noqa: F401
+    PathInfo,
+    PathStepInfo,
+    SlicedContractorC64,
+    SlicedContractorC128,
+    TaskBasedContractorC64,
+    TaskBasedContractorC128,
+    TensorC64,
+    TensorC128,
+    TensorNetworkC64,
+    TensorNetworkC128,
+    TensorNetworkFileC64,
+    TensorNetworkFileC128,
+    TensorNetworkSerializerC64,
+    TensorNetworkSerializerC128,
+    add_tensors,
+    conj,
+    contract_tensors,
+    reshape,
+    slice_index,
+    transpose,
+    version,
+)
+
+__all__ = [
+    "PathInfo", "PathStepInfo", "add_tensors", "conj", "contract_tensors", "reshape", "slice_index", "transpose",
+    "version", "TaskBasedContractorType", "TensorType", "TensorNetworkType", "TensorNetworkFileType",
+    "TensorNetworkSerializerType", "TaskBasedContractor", "Tensor", "TensorNetwork", "TensorNetworkFile",
+    "TensorNetworkSerializer", "SlicedContractor",
+]
+
+TaskBasedContractorType = Union[TaskBasedContractorC64, TaskBasedContractorC128]
+TensorType = Union[TensorC64, TensorC128]
+TensorNetworkType = Union[TensorNetworkC64, TensorNetworkC128]
+TensorNetworkFileType = Union[TensorNetworkFileC64, TensorNetworkFileC128]
+TensorNetworkSerializerType = Union[TensorNetworkSerializerC64, TensorNetworkSerializerC128]
+
+
+def _pick(c64, c128, args, kwargs):
+    dtype = np.dtype(kwargs.pop("dtype", np.complex128))
+    if dtype == np.complex64:
+        return c64(*args, **kwargs)
+    if dtype == np.complex128:
+        return c128(*args, **kwargs)
+    raise TypeError(f"Data type '{dtype}' is not supported.")
+
+
+def TaskBasedContractor(*args, **kwargs) -> TaskBasedContractorType:
+    return _pick(TaskBasedContractorC64, TaskBasedContractorC128, args, kwargs)
+
+
+def Tensor(*args, **kwargs) -> TensorType:
+    return _pick(TensorC64, TensorC128, args, kwargs)
+
+
+def TensorNetwork(*args, **kwargs) -> TensorNetworkType:
+    return _pick(TensorNetworkC64, TensorNetworkC128, args, kwargs)
+
+
+def TensorNetworkFile(*args, **kwargs) -> TensorNetworkFileType:
+    return _pick(TensorNetworkFileC64, TensorNetworkFileC128, args, kwargs)
+
+
+def TensorNetworkSerializer(*args, **kwargs) -> TensorNetworkSerializerType:
+    return _pick(TensorNetworkSerializerC64, TensorNetworkSerializerC128, args, kwargs)
+
+
+def SlicedContractor(*args, **kwargs):
+    """B200 extension: device-resident contraction of a sliced network (jb_plan)."""
+    return _pick(SlicedContractorC64, SlicedContractorC128, args, kwargs)
+
+
+__version__ = version()
