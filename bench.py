@@ -203,6 +203,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from jet_b200 import ContractionPlan
+    from jet_b200.distributed import reduce_amplitude
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,7 +235,6 @@ def run_ours(args):
     leaves = [torch.from_numpy(np.ascontiguousarray(arr)).pin_memory() for _, arr in net.tensors]
     leaf_ptrs = [t.data_ptr() for t in leaves]
     h2d_bytes = int(sum(t.numel() * t.element_size() for t in leaves))
-    partial = torch.zeros(2 * plan.result_elems, dtype=torch.float64, device=f"cuda:{local}")
 
     # ---- device-resident arm -------------------------------------------------------------
     plan.reset()
@@ -251,10 +251,8 @@ def run_ours(args):
     for k in range(args.steps):
         plan.run_list(slice_ids(args.warmup + k))
     if world > 1:
-        # the one exchange step: NCCL reduce of the partial amplitudes to rank 0
-        res = plan.result()  # waits for this rank's slices
-        partial.copy_(torch.from_numpy(res.reshape(-1).view(np.float64)))
-        dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM)
+        # the one exchange step: NCCL reduce of the FP64 partial amplitudes to rank 0
+        reduce_amplitude(plan.result(), dst=0, device=torch.device("cuda", local))
     cur = torch.cuda.current_stream()
     cur.wait_stream(stream)
     e1.record(cur)
@@ -284,8 +282,7 @@ def run_ours(args):
         plan.run_list(slice_ids(args.warmup + k))
         r = plan.result()            # D2H of the step's accumulated amplitude (syncs)
     if world > 1:
-        partial.copy_(torch.from_numpy(r.reshape(-1).view(np.float64)))
-        dist.reduce(partial, dst=0, op=dist.ReduceOp.SUM)
+        reduce_amplitude(r, dst=0, device=torch.device("cuda", local))
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
