@@ -37,8 +37,28 @@ WORKLOADS = {
     "sycamore53_m12_s9": ("m12.json", "h5 m H10 w y J S G10 P0".split(), "complex64"),
     "sycamore53_m10_s6": ("m10.json", "p7 s7 h4 m1 m2 I2".split(), "complex64"),
     "sycamore53_m10_s10": ("m10.json", "p7 s7 h4 m1 m2 I2 V4 z2 t4 C1".split(), "complex64"),
+    # GBS (BASELINE config 5): the reference ships no slice set for these files
+    # (examples/paper_benchmarks/CPU/jet_cpu_gbs/jet_gbs_full.cpp contracts unsliced), so the sliced
+    # indices are chosen by the greedy slicer (jet_b200/slicing.py): ("auto", number of indices)
+    "gbs_fock4_total10_s2": ("gbs_dim2_nc1_lw8_rp5_fock4_total10_0.kraken.json", ("auto", 2), "complex128"),
+    "gbs_fock8_total0_s2": ("gbs_dim2_nc1_lw8_rp5_fock8_total0_0.kraken.json", ("auto", 2), "complex128"),
 }
-METRIC = "sliced Sycamore-53 amplitude slices/s"
+
+
+def resolve_sliced(workload):
+    """The workload's sliced-index list (running the greedy slicer for ("auto", n) entries)."""
+    fn, sliced, dt = WORKLOADS[workload]
+    if isinstance(sliced, tuple) and sliced[0] == "auto":
+        from jet_b200.slicing import find_slices
+        js = json.load(open(os.path.join(DATA_DIR, fn)))
+        leaf = [t[1] for t in js["tensors"]]
+        dims = {}
+        for t in js["tensors"]:
+            for i, d in zip(t[1], t[2]):
+                dims[i] = d
+        return find_slices(leaf, dims, [tuple(p) for p in js["path"]], [], extra=sliced[1])
+    return list(sliced)
+METRIC = "sliced Sycamore-53 amplitude slices/s"  # for the gbs_* workloads: sliced GBS amplitude slices/s
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -113,7 +133,8 @@ class ClockSampler:
 
 def load_network(workload):
     from jet_b200 import NetworkFile
-    fn, sliced, dt = WORKLOADS[workload]
+    fn, _, dt = WORKLOADS[workload]
+    sliced = resolve_sliced(workload)
     path = os.path.join(DATA_DIR, fn)
     if not os.path.exists(path):
         raise SystemExit(f"{path} missing: run `make -C oracle` where /root/reference exists")
@@ -133,7 +154,8 @@ def cpu_reference_sample(workload, budget_s=20.0):
     from oracle import ref
     if not ref.available():
         return None
-    fn, sliced, dt = WORKLOADS[workload]
+    fn, _, dt = WORKLOADS[workload]
+    sliced = resolve_sliced(workload)
     text = open(os.path.join(DATA_DIR, fn)).read()
     js = json.loads(text)
     leaf = [t[1] for t in js["tensors"]]
@@ -183,11 +205,13 @@ def run_reference(args):
         if sum(r["wall_s"] for r in t_all) > 150:
             break
     value = float(np.mean([r["value"] for r in t_all]))
-    fn, sliced, dt = WORKLOADS[args.workload]
+    fn, _, dt = WORKLOADS[args.workload]
+    sliced = resolve_sliced(args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": args.gpus,
         "steps": len(t_all), "warmup": args.warmup, "ms_per_step": float(np.mean([r["seconds"] for r in t_all]) * 1e3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "reference data file " + fn,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dt == "complex64" else "f64",
+        "data": "reference data file " + fn,
         "config": {"workload": args.workload, "sliced_indices": sliced, "network": fn},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -334,7 +358,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": f"reference data file {fn} (Sycamore-53 network + path), slice ids synthetic",
+            "vs_baseline": None, "dtype": "f32" if dt == "complex64" else "f64",
+            "data": f"reference data file {fn} (network + path), slice ids synthetic",
             "config": {"workload": args.workload, "network": fn, "sliced_indices": sliced, "num_slices": total,
                        "slices_per_step_per_gpu": sps, "steps_per_slice": int(st.steps_total - st.steps_shared),
                        "l2": "per-slice working set (%.1f GB algorithmic) exceeds L2; no flush needed" % (st.bytes_per_slice / 1e9),

@@ -19,6 +19,7 @@
 //      (GemmKernel, FP32/FP64 FMA, shared-memory tiled, deterministic split-K).  Used when both
 //      operands are large, for non-power-of-two extents, and for the GEMV / DOTU corners.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -454,8 +455,19 @@ int GridFor(long long n)
 // =================================================================================================
 // Host API
 // =================================================================================================
+static bool TcEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_DISABLE_TC");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
+}
+
 size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k)
 {
+    if (TcEnabled() && GemmTcEligible(dtype, m, n, k))
+        return GemmTcWorkspaceBytes(n, k);
     const GemmConfig cfg = ChooseGemm(m, n, k);
     if (cfg.splits <= 1)
         return 0;
@@ -466,6 +478,8 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
                void *ws, size_t ws_bytes, cudaStream_t stream)
 {
     JB_REQUIRE(m >= 1 && n >= 1 && k >= 1, "gemm: dimensions must be positive");
+    if (TcEnabled() && GemmTcEligible(dtype, m, n, k) && ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(n, k))
+        return LaunchGemmTc(m, n, k, a, b, c, ws, ws_bytes, stream);
     if (dtype == JB_C64)
         return LaunchGemmT<float>(m, n, k, a, b, c, ws, ws_bytes, stream);
     if (dtype == JB_C128)
@@ -704,7 +718,7 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
     P.ws_gemm_off = off;
     P.ws_gemm_bytes = GemmWorkspaceBytes(dtype, P.m, P.n, P.k);
     if (P.ws_gemm_bytes > 0)
-        P.launches++;
+        P.launches++; // split-K reduce, or the B expansion of the tensor-core path
     off += align(P.ws_gemm_bytes);
     P.ws_bytes = off;
     return 0;

@@ -12,14 +12,15 @@ from typing import Dict, List, Sequence, Tuple
 
 def replay(leaf_indices: Sequence[Sequence[str]], dims: Dict[str, int], path: Sequence[Tuple[int, int]],
            sliced: Sequence[str] = ()):
-    """Returns (jet_flops, max_elems, biggest_node_indices): 2*M*N*K summed over the steps
-    (PathInfo::GetPathStepFlops convention, include/jet/PathInfo.hpp:157-183), the largest
-    intermediate and its indices."""
+    """Returns (jet_flops, max_elems, candidates): 2*M*N*K summed over the steps
+    (PathInfo::GetPathStepFlops convention, include/jet/PathInfo.hpp:157-183), the size of the
+    largest intermediate and the indices of all intermediates of that size."""
     sl = set(sliced)
     nodes: List[List[str]] = [[i for i in idx if i not in sl] for idx in leaf_indices]
     flops = 0.0
     max_elems = 0
     biggest: List[str] = []
+    sizes = []
     for a, b in path:
         A, B = nodes[a], nodes[b]
         sb = set(B)
@@ -35,8 +36,17 @@ def replay(leaf_indices: Sequence[Sequence[str]], dims: Dict[str, int], path: Se
         flops += 2.0 * size * k
         if size > max_elems:
             max_elems = size
-            biggest = out
+        sizes.append(size)
         nodes.append(out)
+    # candidate indices to slice next: every index of every largest intermediate
+    seen = set()
+    n_leaves = len(leaf_indices)
+    for s, size in enumerate(sizes):
+        if size == max_elems:
+            for i in nodes[n_leaves + s]:
+                if i not in seen:
+                    seen.add(i)
+                    biggest.append(i)
     return flops, max_elems, biggest
 
 

@@ -222,3 +222,48 @@ def test_add_and_slice(ops):
         t = rand_c(rng, 2 * 3 * 4 * 5, dtype).reshape(2, 3, 4, 5)
         for ax in range(4):
             assert np.array_equal(ops.slice_index(t, ax, 1), np.take(t, 1, axis=ax))
+
+
+# ---------------------------------------------------------------- tensor-core GEMM (tcgen05, 3xTF32)
+def test_gemm_tensor_core_shapes_vs_fp64(ops):
+    """Shapes eligible for the tcgen05 3xTF32 kernel (M % 128 == 0, N % 64 == 0, K % 16 == 0,
+    K >= 64): complex64 result within 1e-5 of the complex128 product (normwise and on the largest
+    elements), i.e. the split keeps FP32-class accuracy."""
+    rng = np.random.default_rng(41)
+    for m, n, k in [(128, 64, 64), (256, 128, 512), (1024, 1024, 1024), (4096, 512, 2048), (128, 4096, 96), (384, 192, 4000 // 16 * 16)]:
+        a = rand_c(rng, m * k, np.complex64).reshape(m, k)
+        b = rand_c(rng, k * n, np.complex64).reshape(k, n)
+        c = ops.gemm(a, b)
+        ref = a.astype(np.complex128) @ b.astype(np.complex128)
+        e = rel_err(c, ref)
+        assert e < 2e-6, (m, n, k, e)
+        big = np.abs(ref) > 0.5 * np.abs(ref).max()
+        assert np.max(np.abs(c[big] - ref[big]) / np.abs(ref[big])) < 1e-5, (m, n, k)
+
+
+def test_gemm_tensor_core_exact_on_small_integers(ops):
+    """Integer data: every partial product and sum is exact in FP32, so the tensor-core path must
+    reproduce the integer result bit for bit (catches layout / swizzle / sign errors)."""
+    rng = np.random.default_rng(43)
+    m, n, k = 256, 192, 320
+    a = (rng.integers(-3, 4, (m, k)) + 1j * rng.integers(-3, 4, (m, k))).astype(np.complex64)
+    b = (rng.integers(-3, 4, (k, n)) + 1j * rng.integers(-3, 4, (k, n))).astype(np.complex64)
+    ref = (a.astype(np.complex128) @ b.astype(np.complex128)).astype(np.complex64)
+    assert np.array_equal(ops.gemm(a, b), ref)
+
+
+def test_contract_both_operands_large_uses_tensor_cores(ops):
+    rng = np.random.default_rng(47)
+    ra = rb = 20
+    c = 10
+    ids_a = list(range(ra))
+    common = sorted(rng.choice(ra, c, replace=False).tolist())
+    ids_b = common + list(range(100, 100 + rb - c))
+    ids_b = [ids_b[i] for i in rng.permutation(rb)]
+    a = rand_c(rng, 2 ** ra, np.complex64).reshape([2] * ra)
+    b = rand_c(rng, 2 ** rb, np.complex64).reshape([2] * rb)
+    info = ops.contract_info(np.complex64, a.shape, ids_a, b.shape, ids_b)
+    assert info.kernel == 1 and info.m == info.n == info.k == 1024
+    out, _ = ops.contract(a, ids_a, b, ids_b)
+    _, ref = jo.contract(([str(i) for i in ids_a], a.astype(np.complex128)), ([str(i) for i in ids_b], b.astype(np.complex128)))
+    assert rel_err(out, ref) < 2e-6
