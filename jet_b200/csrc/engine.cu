@@ -352,6 +352,8 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         auto it = mode_dim.find(m);
         JB_REQUIRE(it != mode_dim.end(), "Sliced index does not exist.");
         p->sliced_dims.push_back(it->second);
+        JB_REQUIRE(p->num_slices <= (int64_t(1) << 62) / it->second,
+                   "plan: more than 2^62 slices (slice ids are 64-bit)");
         p->num_slices *= it->second;
     }
     auto is_sliced = [&](int32_t m) {
@@ -476,11 +478,13 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     p->ws_bytes = ws_max;
     p->ws_off = alloc.Alloc(std::max<size_t>(ws_max, 512));
     p->acc_off = alloc.Alloc(sizeof(double2) * p->result_elems);
-    p->store_cap = (d->flags & JB_PLAN_STORE_RESULTS) ? p->num_slices : 0;
+    // per-slice result store / explicit slice-id lists hold at most 2^16 entries per run
+    constexpr int64_t kMaxListed = 1 << 16;
+    p->store_cap = (d->flags & JB_PLAN_STORE_RESULTS) ? std::min<int64_t>(p->num_slices, kMaxListed) : 0;
     if (p->store_cap > 0)
         p->store_off = alloc.Alloc(p->eb * p->result_elems * p->store_cap);
     p->state_off = alloc.Alloc(sizeof(DeviceState));
-    p->list_cap = std::max<int64_t>(p->num_slices, 1);
+    p->list_cap = std::max<int64_t>(std::min<int64_t>(p->num_slices, kMaxListed), 1);
     p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
     p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
     for (size_t e = 0; e < exec.size(); e++) {
@@ -642,7 +646,7 @@ int jb_plan_run(jb_plan *p, int64_t first_slice, int64_t count)
 int jb_plan_run_list(jb_plan *p, const int64_t *ids, int64_t count)
 {
     JB_REQUIRE(p && (ids || count == 0), "plan: null argument");
-    JB_REQUIRE(count <= p->list_cap, "plan: slice list longer than the number of slices");
+    JB_REQUIRE(count <= p->list_cap, "plan: slice list too long (at most 65536 ids per call)");
     for (int64_t i = 0; i < count; i++)
         JB_REQUIRE(ids[i] >= 0 && ids[i] < p->num_slices, "plan: slice id out of bounds");
     JB_CUDA(cudaSetDevice(p->device));

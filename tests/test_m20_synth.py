@@ -1,0 +1,77 @@
+"""The synthetic Sycamore-53 m=20 input (BASELINE config 4): the generator is validated against an
+independent brute-force state-vector simulation on small lattices (CPU), the committed m=20 file
+is checked for consistency with its generator (CPU), and one slice is contracted on the GPU and
+compared with the reference engine's result on the same file (golden)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import sycamore_gen as sg  # noqa: E402
+from oracle import jet_oracle as jo  # noqa: E402
+
+DATA = os.path.join(ROOT, "data")
+
+
+@pytest.mark.parametrize("rows,cols,removed,cycles,seed", [(3, 3, None, 6, 1), (4, 3, (0, 0), 8, 2), (2, 2, None, 4, 3),
+                                                          (3, 4, (2, 3), 5, 4)])
+def test_generator_matches_statevector(rows, cols, removed, cycles, seed):
+    sites, ops, bits, leaves, path, meta = sg.build(rows, cols, removed, cycles, seed, trials=3, target_log2=6)
+    want = sg.amplitude_statevector(sites, ops, bits)
+    net = jo.Network([(idx, np.asarray(arr, dtype=np.complex128)) for _, idx, arr in leaves], path)
+    assert abs(complex(net.contract()[1]) - want) < 1e-12
+    if meta["sliced_indices"]:
+        got = jo.amplitude(net, meta["sliced_indices"]).reshape(-1)[0]
+        assert abs(got - want) < 1e-12
+        assert meta["log2_peak_per_slice"] <= 6
+
+
+def test_lattice_is_sycamore_sized():
+    sites, couplers = sg.lattice(9, 6, (0, 0))
+    assert len(sites) == 53
+    assert sum(len(v) for v in couplers.values()) in (86, 87, 88)
+    for cls in couplers.values():  # a class never uses a qubit twice
+        used = [s for pair in cls for s in pair]
+        assert len(used) == len(set(used))
+
+
+def test_committed_m20_file_is_reproducible():
+    meta = json.load(open(os.path.join(DATA, "syc53_m20_seed1.meta.json")))
+    js = json.load(open(os.path.join(DATA, "syc53_m20_seed1.json")))
+    assert meta["qubits"] == 53 and meta["cycles"] == 20 and len(js["tensors"]) == meta["leaves"] == 870
+    assert len(js["path"]) == 869 and meta["log2_num_slices"] == 58 and meta["log2_peak_per_slice"] <= 28
+    sites, ops = sg.circuit(9, 6, (0, 0), 20, 1)
+    leaves = sg.to_network(sites, ops, meta["bits"])
+    for k in (0, 100, 869):
+        assert js["tensors"][k][1] == leaves[k][1]
+        got = np.array([complex(a, b) for a, b in js["tensors"][k][3]])
+        assert np.allclose(got, np.asarray(leaves[k][2]).reshape(-1), atol=1e-7)
+    from jet_b200.slicing import replay
+    leaf = [t[1] for t in js["tensors"]]
+    dims = {i: 2 for idx in leaf for i in idx}
+    flops, mx, _ = replay(leaf, dims, [tuple(p) for p in js["path"]], meta["sliced_indices"])
+    assert mx == 2 ** 28 and flops == meta["jet_flops_per_slice"]
+
+
+@pytest.mark.gpu
+def test_m20_slice_matches_reference_golden():
+    from jet_b200 import ContractionPlan, NetworkFile
+    gpath = os.path.join(DATA, "syc53_m20_seed1.golden.json")
+    if not os.path.exists(gpath):
+        pytest.skip("m=20 golden not generated")
+    gold = json.load(open(gpath))
+    meta = json.load(open(os.path.join(DATA, "syc53_m20_seed1.meta.json")))
+    net = NetworkFile.load(os.path.join(DATA, "syc53_m20_seed1.json"), np.complex64)
+    with ContractionPlan(net, meta["sliced_indices"], store_results=True) as plan:
+        assert plan.num_slices == 2 ** 58
+        ids = [int(k) for k in gold]
+        plan.reset()
+        plan.run_list(ids)
+        for n, k in enumerate(gold):
+            want = complex(gold[k]["re"], gold[k]["im"])
+            got = plan.slice_result(n).reshape(-1)[0]
+            assert abs(got - want) / abs(want) < 1e-5, (k, got, want)
