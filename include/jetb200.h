@@ -97,6 +97,47 @@ int jb_contract(int dtype, int rank_a, const int64_t *extent_a, const int32_t *m
                 const void *d_a, int rank_b, const int64_t *extent_b, const int32_t *modes_b,
                 const void *d_b, void *d_c, void *d_ws, size_t ws_bytes, void *stream);
 
+/* ---- fused contraction chain ------------------------------------------------------------------
+ * Replaces a RUN of Tensor::ContractTensors calls (include/jet/Tensor.hpp:709-752) of the kind
+ * TensorNetwork::Contract issues on consecutive path steps (include/jet/TensorNetwork.hpp:301-328,
+ * 394-421): X_i = ContractTensors(X_{i-1}, R_i) when x_is_left[i] != 0, else
+ * ContractTensors(R_i, X_{i-1}), for i = 1..n_steps, with every R_i small (<= 256 elements, at
+ * most 16 contracted and 16 free values) and all extents powers of two.  One kernel launch keeps
+ * the intermediates X_1..X_{k-1} in shared memory; only X_0 and the R_i are read and X_k written.
+ * The result (labels, extents, values within FMA rounding) equals the step-by-step calls.
+ * jb_chain_info fails (non-zero, message "chain: ...") when the run does not fit one on-chip tile;
+ * callers then split the run or fall back to jb_contract per step. */
+typedef struct jb_chain_desc_t {
+    int32_t dtype;
+    int32_t n_steps;
+    int32_t rank_x;
+    const int64_t *extent_x; /* [rank_x] */
+    const int32_t *modes_x;  /* [rank_x] */
+    const int32_t *rank_r;   /* [n_steps] */
+    const int64_t *extent_r; /* [sum rank_r] */
+    const int32_t *modes_r;  /* [sum rank_r] */
+    const int32_t *x_is_left; /* [n_steps] */
+} jb_chain_desc_t;
+
+typedef struct jb_chain_info_t {
+    int32_t rank_c;
+    int32_t modes_c[JB_MAX_RANK];
+    int64_t extent_c[JB_MAX_RANK];
+    int32_t log_tile;      /* the on-chip tile holds 2^log_tile elements */
+    int32_t conflict_free; /* 1 if every shared-memory phase is bank-conflict-free by construction */
+    int32_t n_stages;      /* barrier-separated stages (runs of K == N steps share one stage) */
+    int32_t pad;
+    double flops;          /* 8*M*N*K summed over the steps */
+    double bytes;          /* sizeof(T)*(|X_0| + sum |R_i| + |X_k|): traffic of the fused launch */
+    double step_bytes;     /* sizeof(T)*(MK+KN+MN) summed over the steps: traffic step by step */
+} jb_chain_info_t;
+
+int jb_chain_info(const jb_chain_desc_t *desc, jb_chain_info_t *info);
+int jb_contract_chain(const jb_chain_desc_t *desc, const void *d_x, const void *const *d_r,
+                      void *d_out, void *stream);
+int jb_contract_chain_host(const jb_chain_desc_t *desc, const void *h_x, const void *const *h_r,
+                           void *h_out);
+
 /* ---- elementwise helpers --------------------------------------------------------------------
  * jb_add: c = a + b elementwise over n complex elements; the aligned-add at the core of
  * Tensor::AddTensors (include/jet/Tensor.hpp:433-451) — permute b first with jb_permute when its
@@ -156,6 +197,7 @@ typedef struct jb_network_desc_t {
 #define JB_PLAN_KEEP_INTERMEDIATES 1 /* no buffer reuse: every step output stays readable */
 #define JB_PLAN_NO_GRAPH 2           /* launch kernels directly instead of through a CUDA graph */
 #define JB_PLAN_STORE_RESULTS 4      /* keep every slice's own result (for GetResults()) */
+#define JB_PLAN_NO_FUSE 8            /* one kernel per path step: no fused contraction chains */
 
 typedef struct jb_plan_stats_t {
     int64_t num_slices;        /* product of sliced extents */
@@ -167,9 +209,12 @@ typedef struct jb_plan_stats_t {
     int32_t steps_shared;      /* slice-independent steps (run once, not per slice) */
     int32_t steps_stream;      /* per-slice steps on the streaming kernel */
     int32_t steps_ttgt;        /* per-slice steps on permute + GEMM */
+    int32_t steps_chained;     /* per-slice steps executed inside fused chains */
+    int32_t chains;            /* fused chains per slice */
     int32_t launches_per_slice; /* kernel launches in one slice's graph */
     double flops_per_slice;    /* 8*M*N*K summed over per-slice steps */
     double bytes_per_slice;    /* sizeof(T)*(MK+KN+MN) summed over per-slice steps */
+    double fused_bytes_per_slice; /* what the launch units of one slice must move (chains fused) */
     double flops_shared, bytes_shared;
     double jet_flops_per_slice; /* 2*M*N*K over ALL steps: PathInfo::GetTotalFlops convention */
     size_t arena_bytes;        /* device memory reserved */
@@ -207,11 +252,30 @@ typedef struct jb_step_info_t {
     int32_t kernel;  /* 0 stream, 1 ttgt */
     int64_t m, n, k;
     double flops, bytes;
+    int32_t op;      /* index of the launch unit (jb_plan_ops) that executes this step */
+    int32_t pad;
 } jb_step_info_t;
 int jb_plan_steps(const jb_plan *plan, jb_step_info_t *steps, int32_t cap, int32_t *count);
 /* Time every per-slice step individually (CUDA events, `reps` repetitions on the given slice);
  * ms[i] is the mean device time of step i (0 for shared steps). */
 int jb_plan_profile(jb_plan *plan, int64_t slice, int reps, float *ms, int32_t cap);
+/* Launch units of one slice in execution order: a unit is one path step or a fused chain of path
+ * steps.  bytes = what the unit must move (for a chain: first input + small operands + last
+ * output); step_bytes = the step-by-step figure sizeof(T)*(MK+KN+MN) summed over its steps. */
+typedef struct jb_op_info_t {
+    int32_t kernel;     /* 0 stream, 1 ttgt, 2 fused chain */
+    int32_t n_steps;    /* path steps executed by this unit */
+    int32_t first_step; /* path index of its first step */
+    int32_t last_step;
+    int32_t log_tile;   /* fused chain: log2 of the shared-memory tile (elements) */
+    int32_t launches;
+    int32_t n_stages;   /* fused chain: barrier-separated stages */
+    int32_t pad;
+    double flops, bytes, step_bytes;
+} jb_op_info_t;
+int jb_plan_ops(const jb_plan *plan, jb_op_info_t *ops, int32_t cap, int32_t *count);
+/* Like jb_plan_profile, per launch unit: ms[i] is the mean device time of unit i. */
+int jb_plan_profile_ops(jb_plan *plan, int64_t slice, int reps, float *ms, int32_t cap);
 
 #ifdef __cplusplus
 }

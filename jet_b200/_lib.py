@@ -17,6 +17,7 @@ JB_MAX_RANK = 64
 JB_PLAN_KEEP_INTERMEDIATES = 1
 JB_PLAN_NO_GRAPH = 2
 JB_PLAN_STORE_RESULTS = 4
+JB_PLAN_NO_FUSE = 8
 
 
 class JetB200Error(RuntimeError):
@@ -64,9 +65,12 @@ class PlanStats(C.Structure):
         ("steps_shared", C.c_int32),
         ("steps_stream", C.c_int32),
         ("steps_ttgt", C.c_int32),
+        ("steps_chained", C.c_int32),
+        ("chains", C.c_int32),
         ("launches_per_slice", C.c_int32),
         ("flops_per_slice", C.c_double),
         ("bytes_per_slice", C.c_double),
+        ("fused_bytes_per_slice", C.c_double),
         ("flops_shared", C.c_double),
         ("bytes_shared", C.c_double),
         ("jet_flops_per_slice", C.c_double),
@@ -87,6 +91,53 @@ class StepInfo(C.Structure):
         ("k", C.c_int64),
         ("flops", C.c_double),
         ("bytes", C.c_double),
+        ("op", C.c_int32),
+        ("pad", C.c_int32),
+    ]
+
+
+class OpInfo(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32),
+        ("n_steps", C.c_int32),
+        ("first_step", C.c_int32),
+        ("last_step", C.c_int32),
+        ("log_tile", C.c_int32),
+        ("launches", C.c_int32),
+        ("n_stages", C.c_int32),
+        ("pad", C.c_int32),
+        ("flops", C.c_double),
+        ("bytes", C.c_double),
+        ("step_bytes", C.c_double),
+    ]
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("n_steps", C.c_int32),
+        ("rank_x", C.c_int32),
+        ("extent_x", C.POINTER(C.c_int64)),
+        ("modes_x", C.POINTER(C.c_int32)),
+        ("rank_r", C.POINTER(C.c_int32)),
+        ("extent_r", C.POINTER(C.c_int64)),
+        ("modes_r", C.POINTER(C.c_int32)),
+        ("x_is_left", C.POINTER(C.c_int32)),
+    ]
+
+
+class ChainInfo(C.Structure):
+    _fields_ = [
+        ("rank_c", C.c_int32),
+        ("modes_c", C.c_int32 * JB_MAX_RANK),
+        ("extent_c", C.c_int64 * JB_MAX_RANK),
+        ("log_tile", C.c_int32),
+        ("conflict_free", C.c_int32),
+        ("n_stages", C.c_int32),
+        ("pad", C.c_int32),
+        ("flops", C.c_double),
+        ("bytes", C.c_double),
+        ("step_bytes", C.c_double),
     ]
 
 
@@ -100,7 +151,8 @@ SYMBOLS = [
     "jb_slice_host", "jb_conj_host", "jb_plan_create", "jb_plan_destroy", "jb_plan_stats", "jb_plan_upload",
     "jb_plan_reset", "jb_plan_run", "jb_plan_run_list", "jb_plan_result", "jb_plan_slice_result",
     "jb_plan_node", "jb_plan_sync", "jb_plan_last_ms", "jb_plan_stream", "jb_plan_steps",
-    "jb_plan_profile",
+    "jb_plan_profile", "jb_plan_ops", "jb_plan_profile_ops", "jb_chain_info", "jb_contract_chain",
+    "jb_contract_chain_host",
 ]
 
 _lib = None
@@ -167,6 +219,12 @@ def lib():
         L.jb_plan_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.jb_plan_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.jb_plan_profile.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int32]
+        L.jb_plan_ops.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.jb_plan_profile_ops.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int32]
+        L.jb_chain_info.argtypes = [C.POINTER(ChainDesc), C.POINTER(ChainInfo)]
+        L.jb_contract_chain.argtypes = [C.POINTER(ChainDesc), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p,
+                                        C.c_void_p]
+        L.jb_contract_chain_host.argtypes = [C.POINTER(ChainDesc), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
         _lib = L
     return _lib
 

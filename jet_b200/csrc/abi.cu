@@ -259,6 +259,102 @@ int jb_contract(int dtype, int rank_a, const int64_t *extent_a, const int32_t *m
     return LaunchContract(P, d_a, d_b, d_c, d_ws, static_cast<cudaStream_t>(stream));
 }
 
+// ---- fused contraction chain ---------------------------------------------------------------------
+namespace {
+int BuildChain(const jb_chain_desc_t *d, ChainOp *op)
+{
+    JB_REQUIRE(d != nullptr, "chain: null argument");
+    JB_REQUIRE(d->dtype == JB_C64 || d->dtype == JB_C128, "chain: unknown dtype");
+    JB_REQUIRE(d->n_steps >= 1, "chain: at least one step is required");
+    JB_REQUIRE(d->rank_x >= 0 && d->rank_x <= JB_MAX_RANK, "chain: rank out of range");
+    std::vector<int32_t> mx(d->modes_x, d->modes_x + d->rank_x);
+    std::vector<int64_t> ex(d->extent_x, d->extent_x + d->rank_x);
+    std::vector<ChainOperand> ops;
+    size_t off = 0;
+    for (int s = 0; s < d->n_steps; s++) {
+        const int r = d->rank_r[s];
+        JB_REQUIRE(r >= 0 && r <= JB_MAX_RANK, "chain: rank out of range");
+        ChainOperand o;
+        o.modes.assign(d->modes_r + off, d->modes_r + off + r);
+        o.extent.assign(d->extent_r + off, d->extent_r + off + r);
+        o.x_is_left = d->x_is_left[s] != 0;
+        off += r;
+        ops.push_back(o);
+    }
+    std::string why;
+    if (MakeChainOp(d->dtype, mx, ex, ops, ChainMaxTileBits(d->dtype), op, &why) != 0)
+        return Fail("chain: " + why);
+    return 0;
+}
+} // namespace
+
+int jb_chain_info(const jb_chain_desc_t *desc, jb_chain_info_t *info)
+{
+    JB_REQUIRE(info, "chain: null argument");
+    ChainOp op;
+    JB_TRY(BuildChain(desc, &op));
+    info->rank_c = static_cast<int32_t>(op.modes_c.size());
+    for (size_t i = 0; i < op.modes_c.size(); i++) {
+        info->modes_c[i] = op.modes_c[i];
+        info->extent_c[i] = op.extent_c[i];
+    }
+    info->log_tile = op.log_tile;
+    info->conflict_free = op.conflict_free;
+    info->n_stages = op.n_stages;
+    info->pad = 0;
+    info->flops = op.flops;
+    info->bytes = op.bytes;
+    info->step_bytes = op.step_bytes;
+    return 0;
+}
+
+int jb_contract_chain(const jb_chain_desc_t *desc, const void *d_x, const void *const *d_r,
+                      void *d_out, void *stream)
+{
+    JB_REQUIRE(d_x && d_r && d_out, "chain: null buffer");
+    ChainOp op;
+    JB_TRY(BuildChain(desc, &op));
+    return LaunchChain(op, d_x, d_r, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int jb_contract_chain_host(const jb_chain_desc_t *desc, const void *h_x, const void *const *h_r,
+                           void *h_out)
+{
+    JB_REQUIRE(h_x && h_r && h_out, "chain: null buffer");
+    ChainOp op;
+    JB_TRY(BuildChain(desc, &op));
+    const size_t eb = ElemBytes(desc->dtype);
+    const size_t bx = eb * static_cast<size_t>(Product(desc->rank_x, desc->extent_x));
+    size_t bout = eb;
+    for (int64_t e : op.extent_c)
+        bout *= static_cast<size_t>(e);
+    DevBuf x(0), out(1), rs(2);
+    JB_TRY(x.Alloc(bx));
+    JB_TRY(out.Alloc(bout));
+    std::vector<size_t> roff(desc->n_steps);
+    size_t rtotal = 0, off = 0;
+    for (int s = 0; s < desc->n_steps; s++) {
+        roff[s] = rtotal;
+        const size_t b = eb * static_cast<size_t>(Product(desc->rank_r[s], desc->extent_r + off));
+        rtotal += (b + 255) & ~size_t(255);
+        off += desc->rank_r[s];
+    }
+    JB_TRY(rs.Alloc(rtotal));
+    JB_CUDA(cudaMemcpy(x.p, h_x, bx, cudaMemcpyHostToDevice));
+    std::vector<const void *> rp(desc->n_steps);
+    off = 0;
+    for (int s = 0; s < desc->n_steps; s++) {
+        const size_t b = eb * static_cast<size_t>(Product(desc->rank_r[s], desc->extent_r + off));
+        off += desc->rank_r[s];
+        JB_REQUIRE(h_r[s] != nullptr, "chain: null buffer");
+        JB_CUDA(cudaMemcpy(static_cast<unsigned char *>(rs.p) + roff[s], h_r[s], b, cudaMemcpyHostToDevice));
+        rp[s] = static_cast<unsigned char *>(rs.p) + roff[s];
+    }
+    JB_TRY(LaunchChain(op, x.p, rp.data(), out.p, nullptr));
+    JB_CUDA(cudaMemcpy(h_out, out.p, bout, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int jb_add(int dtype, int64_t n, const void *d_a, const void *d_b, void *d_c, void *stream)
 {
     return LaunchAdd(dtype, n, d_a, d_b, d_c, static_cast<cudaStream_t>(stream));

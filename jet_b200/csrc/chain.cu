@@ -1,0 +1,621 @@
+// K3 — fused contraction chain.
+//
+// Replaces a RUN of Tensor::ContractTensors calls (reference: include/jet/Tensor.hpp:709-752) issued
+// by TensorNetwork::Contract / TaskBasedContractor on consecutive path steps
+// (include/jet/TensorNetwork.hpp:301-328, include/jet/TaskBasedContractor.hpp:386-390) in which each
+// result is contracted next with a small tensor.  The reference (and one StreamContractKernel launch
+// per step) moves the large intermediate through memory once per step; this kernel moves it once
+// per CHAIN: a tile that contains every address bit the chain contracts or creates is loaded into
+// shared memory, all steps are applied in place (FP32 / FP64 FMA, same association as the
+// step-by-step contraction: sum over k per step), and only the final tensor is stored.
+// See chain_plan.h for the tile construction; the kernel below is an interpreter of its GF(2)-linear
+// index maps.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "chain_plan.h"
+#include "common.cuh"
+
+namespace jb {
+
+struct ChainPtrs {
+    const void *r[kChainMaxSteps];
+};
+
+namespace {
+
+constexpr int kChainThreads = 256;
+constexpr int kLogChainThreads = 8;
+
+template <typename R> struct Cplx;
+template <> struct Cplx<float> {
+    using type = float2;
+};
+template <> struct Cplx<double> {
+    using type = double2;
+};
+
+template <typename C> __device__ __forceinline__ void CMulAdd(C &acc, const C a, const C b)
+{
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+
+__device__ __forceinline__ unsigned Lin(unsigned idx, const uint16_t *col, int nbits)
+{
+    unsigned r = 0;
+    for (int q = 0; q < nbits; q++)
+        if ((idx >> q) & 1u)
+            r ^= col[q];
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long Deposit(unsigned long long idx, const uint8_t *bit,
+                                                      int nbits)
+{
+    unsigned long long r = 0;
+    for (int q = 0; q < nbits; q++)
+        r |= ((idx >> q) & 1ull) << bit[q];
+    return r;
+}
+
+// One contraction step applied in place to the tile.  A "group" is one assignment of the tile bits
+// the step does not contract; its K inputs are read into registers, the N outputs are written to
+// the positions of the new bits.  KC = K (all k values in registers), G = groups in flight.
+template <typename R, int KC, int G>
+__device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ tile,
+                                          const typename Cplx<R>::type *__restrict__ Bm,
+                                          const ChainStepParams &q,
+                                          const unsigned *__restrict__ gtab, const int tid)
+{
+    using C = typename Cplx<R>::type;
+    const int log_g = q.log_g;
+    const int log_n = q.log_n;
+    const int N = 1 << log_n;
+    const int np = q.np;
+    unsigned koff[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) {
+        unsigned r = 0;
+#pragma unroll
+        for (int b = 0; (1 << b) < KC; b++)
+            if (kk & (1 << b))
+                r ^= q.kcol[b];
+        koff[kk] = r;
+    }
+    unsigned noff_lo[4];
+    noff_lo[0] = 0;
+    noff_lo[1] = log_n >= 1 ? q.ncol[0] : 0u;
+    noff_lo[2] = log_n >= 2 ? q.ncol[1] : 0u;
+    noff_lo[3] = noff_lo[1] ^ noff_lo[2];
+    const unsigned ncol2 = log_n >= 3 ? q.ncol[2] : 0u;
+    const unsigned ncol3 = log_n >= 4 ? q.ncol[3] : 0u;
+
+    const int tid_bits = log_g < kLogChainThreads ? log_g : kLogChainThreads;
+    const unsigned a_tid = Lin(static_cast<unsigned>(tid), q.gcol, tid_bits);
+    const bool t_ok = tid < (1 << log_g);
+    const int per_thread = log_g > kLogChainThreads ? (1 << (log_g - kLogChainThreads)) : 1;
+    const C *bbase = Bm + q.b_off;
+
+    for (int j0 = 0; j0 < per_thread; j0 += G) {
+        unsigned base[G];
+        bool ok[G];
+        C a[G][KC];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int j = j0 + g;
+            ok[g] = t_ok && j < per_thread;
+            base[g] = a_tid ^ gtab[j & 31];
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++)
+                a[g][kk] = ok[g] ? tile[base[g] ^ koff[kk]] : C{R(0), R(0)};
+        }
+        for (int y0 = 0; y0 < N; y0 += 4) {
+            const unsigned nhi = ((y0 & 4) ? ncol2 : 0u) ^ ((y0 & 8) ? ncol3 : 0u);
+            C acc[G][4];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+                    acc[g][yy] = C{R(0), R(0)};
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                const C *brow = bbase + kk * np + y0;
+                C r[4];
+                if constexpr (sizeof(C) == 8) {
+                    const float4 v0 = *reinterpret_cast<const float4 *>(brow);
+                    const float4 v1 = *reinterpret_cast<const float4 *>(brow + 2);
+                    r[0] = C{v0.x, v0.y};
+                    r[1] = C{v0.z, v0.w};
+                    r[2] = C{v1.x, v1.y};
+                    r[3] = C{v1.z, v1.w};
+                }
+                else {
+#pragma unroll
+                    for (int yy = 0; yy < 4; yy++)
+                        r[yy] = brow[yy];
+                }
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        CMulAdd(acc[g][yy], a[g][kk], r[yy]);
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (!ok[g])
+                    continue;
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+                    if (y0 + yy < N)
+                        tile[base[g] ^ nhi ^ noff_lo[yy]] = acc[g][yy];
+            }
+        }
+    }
+}
+
+// ---- register stage -------------------------------------------------------------------------------
+// E holds the 16 elements spanned by the stage's 4 local tile positions.  A step contracts the local
+// bits in MASK (k bit q <-> q-th lowest set bit of MASK) and re-creates as many new bits in the same
+// places: out[g | spread(n)] = sum_k in[g | spread(k)] * B[k][n] for every assignment g of the other
+// local bits.  All register indices are compile-time constants.
+template <int MASK> __device__ __forceinline__ constexpr int Spread(int v)
+{
+    int r = 0, q = 0;
+    for (int b = 0; b < kChainLocalBits; b++)
+        if (MASK & (1 << b)) {
+            if (v & (1 << q))
+                r |= 1 << b;
+            q++;
+        }
+    return r;
+}
+
+// NL local bits: 4 for complex64 (16 elements = 32 registers), 3 for complex128.
+template <typename R, int NL, int MASK>
+__device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
+                                           const typename Cplx<R>::type *__restrict__ B, const int np)
+{
+    using C = typename Cplx<R>::type;
+    constexpr int LK = ((MASK >> 0) & 1) + ((MASK >> 1) & 1) + ((MASK >> 2) & 1) + ((MASK >> 3) & 1);
+    constexpr int K = 1 << LK;
+    constexpr int NE = 1 << NL;
+    C out[NE];
+#pragma unroll
+    for (int e = 0; e < NE; e++)
+        out[e] = C{R(0), R(0)};
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+#pragma unroll
+        for (int n = 0; n < K; n++) {
+            const C r = B[k * np + n];
+#pragma unroll
+            for (int g = 0; g < NE; g++) {
+                if (g & MASK)
+                    continue;
+                CMulAdd(out[g | Spread<MASK>(n)], E[g | Spread<MASK>(k)], r);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; e++)
+        E[e] = out[e];
+}
+
+template <typename R, int NL>
+__device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1 << NL],
+                                                   const typename Cplx<R>::type *__restrict__ B,
+                                                   const int np, const int mask)
+{
+    if constexpr (NL == 4) {
+        switch (mask) {
+        case 1: ApplyLocal<R, NL, 1>(E, B, np); break;
+        case 2: ApplyLocal<R, NL, 2>(E, B, np); break;
+        case 3: ApplyLocal<R, NL, 3>(E, B, np); break;
+        case 4: ApplyLocal<R, NL, 4>(E, B, np); break;
+        case 5: ApplyLocal<R, NL, 5>(E, B, np); break;
+        case 6: ApplyLocal<R, NL, 6>(E, B, np); break;
+        case 7: ApplyLocal<R, NL, 7>(E, B, np); break;
+        case 8: ApplyLocal<R, NL, 8>(E, B, np); break;
+        case 9: ApplyLocal<R, NL, 9>(E, B, np); break;
+        case 10: ApplyLocal<R, NL, 10>(E, B, np); break;
+        case 11: ApplyLocal<R, NL, 11>(E, B, np); break;
+        case 12: ApplyLocal<R, NL, 12>(E, B, np); break;
+        case 13: ApplyLocal<R, NL, 13>(E, B, np); break;
+        case 14: ApplyLocal<R, NL, 14>(E, B, np); break;
+        default: ApplyLocal<R, NL, 15>(E, B, np); break;
+        }
+    }
+    else {
+        switch (mask) {
+        case 1: ApplyLocal<R, NL, 1>(E, B, np); break;
+        case 2: ApplyLocal<R, NL, 2>(E, B, np); break;
+        case 3: ApplyLocal<R, NL, 3>(E, B, np); break;
+        case 4: ApplyLocal<R, NL, 4>(E, B, np); break;
+        case 5: ApplyLocal<R, NL, 5>(E, B, np); break;
+        case 6: ApplyLocal<R, NL, 6>(E, B, np); break;
+        default: ApplyLocal<R, NL, 7>(E, B, np); break;
+        }
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__restrict__ tile,
+                                                   const typename Cplx<R>::type *__restrict__ Bm,
+                                                   const ChainParams &p, const ChainStageParams &g,
+                                                   const unsigned *__restrict__ gtab, const int tid)
+{
+    using C = typename Cplx<R>::type;
+    constexpr int NL = sizeof(R) == 4 ? 4 : 3;
+    constexpr int NE = 1 << NL;
+    const int log_g = g.log_g;
+    const int tid_bits = log_g < kLogChainThreads ? log_g : kLogChainThreads;
+    if (tid >= (1 << log_g))
+        return;
+    const unsigned a_tid = Lin(static_cast<unsigned>(tid), g.gcol, tid_bits);
+    const int per_thread = log_g > kLogChainThreads ? (1 << (log_g - kLogChainThreads)) : 1;
+    unsigned l01[4], l23[4];
+    l01[0] = 0;
+    l01[1] = g.lcol[0];
+    l01[2] = g.lcol[1];
+    l01[3] = l01[1] ^ l01[2];
+    l23[0] = 0;
+    l23[1] = g.lcol[2];
+    l23[2] = NL == 4 ? g.lcol[3] : 0u;
+    l23[3] = l23[1] ^ l23[2];
+    for (int j = 0; j < per_thread; j++) {
+        const unsigned base = a_tid ^ gtab[j];
+        C E[NE];
+#pragma unroll
+        for (int e = 0; e < NE; e++)
+            E[e] = tile[base ^ l01[e & 3] ^ l23[e >> 2]];
+        for (int t = 0; t < g.count; t++) {
+            const ChainStepParams &q = p.step[g.first + t];
+            ApplyLocalDispatch<R, NL>(E, Bm + q.b_off, q.np, g.mask[t]);
+        }
+#pragma unroll
+        for (int e = 0; e < NE; e++)
+            tile[base ^ l01[e & 3] ^ l23[e >> 2]] = E[e];
+    }
+}
+
+// shared-memory tables of the thread-independent parts of the index maps (built once per CTA)
+struct ChainTables {
+    unsigned long long in_g[32], out_g[32];
+    unsigned in_s[32], out_s[32];
+    unsigned stage_g[kChainMaxSteps][32];
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kChainThreads, 2)
+    ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
+                typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
+                const __grid_constant__ ChainPtrs rp)
+{
+    using C = typename Cplx<R>::type;
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    C *tile = reinterpret_cast<C *>(chain_smem);
+    C *Bm = tile + (1 << p.log_tile);
+    ChainTables &tab = *reinterpret_cast<ChainTables *>(Bm + ((p.resident_elems + 1) & ~1));
+    const int tid = threadIdx.x;
+
+    // resident operands -> shared memory as K x np matrices (columns n >= N are zero)
+    for (int s = 0; s < p.n_steps; s++) {
+        const ChainStepParams &q = p.step[s];
+        const C *Rs = static_cast<const C *>(rp.r[s]);
+        const int np = q.np;
+        const int N = 1 << q.log_n;
+        const int total = np << q.log_k;
+        for (int e = tid; e < total; e += kChainThreads) {
+            const unsigned k = e / np, n = e % np;
+            C v = C{R(0), R(0)};
+            if (static_cast<int>(n) < N)
+                v = __ldg(Rs + (Deposit(k, q.rk, q.log_k) | Deposit(n, q.rn, q.log_n)));
+            Bm[q.b_off + e] = v;
+        }
+    }
+
+    const int in_tid_bits = min(p.log_tile_in, kLogChainThreads);
+    const int out_tid_bits = min(p.log_tile_out, kLogChainThreads);
+    if (tid < 32) {
+        tab.in_g[tid] = Deposit(tid, p.in_gbit + kLogChainThreads, p.log_tile_in - in_tid_bits);
+        tab.in_s[tid] = Lin(tid, p.in_scol + kLogChainThreads, p.log_tile_in - in_tid_bits);
+        tab.out_g[tid] = Deposit(tid, p.out_gbit + kLogChainThreads, p.log_tile_out - out_tid_bits);
+        tab.out_s[tid] = Lin(tid, p.out_scol + kLogChainThreads, p.log_tile_out - out_tid_bits);
+    }
+    for (int e = tid; e < p.n_stages * 32; e += kChainThreads) {
+        const int st = e >> 5, j = e & 31;
+        const ChainStageParams &g = p.stage[st];
+        unsigned v;
+        if (g.kind == 1) {
+            const int tb = min(static_cast<int>(g.log_g), kLogChainThreads);
+            v = Lin(j, g.gcol + kLogChainThreads, g.log_g - tb);
+        }
+        else {
+            const ChainStepParams &q = p.step[g.first];
+            const int tb = min(static_cast<int>(q.log_g), kLogChainThreads);
+            v = Lin(j, q.gcol + kLogChainThreads, q.log_g - tb);
+        }
+        tab.stage_g[st][j] = v;
+    }
+
+    // per-thread parts of the load / store index maps (tile independent)
+    const unsigned in_s_tid = Lin(tid, p.in_scol, in_tid_bits);
+    const unsigned out_s_tid = Lin(tid, p.out_scol, out_tid_bits);
+    const unsigned long long in_g_tid = Deposit(tid, p.in_gbit, in_tid_bits);
+    const unsigned long long out_g_tid = Deposit(tid, p.out_gbit, out_tid_bits);
+    const bool in_ok = tid < (1 << p.log_tile_in);
+    const bool out_ok = tid < (1 << p.log_tile_out);
+    const int in_iters = p.log_tile_in > kLogChainThreads ? 1 << (p.log_tile_in - kLogChainThreads) : 1;
+    const int out_iters = p.log_tile_out > kLogChainThreads ? 1 << (p.log_tile_out - kLogChainThreads) : 1;
+    __syncthreads();
+
+    constexpr int U = 8;
+    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const unsigned long long in_base = Deposit(static_cast<unsigned long long>(t), p.outer_in, p.log_outer);
+        const unsigned long long out_base = Deposit(static_cast<unsigned long long>(t), p.outer_out, p.log_outer);
+
+        // ---- load: X_0 tile -> shared memory (coalesced along the low X_0 address bits) ----------
+        if (in_ok) {
+            const C *src = X0 + (in_base | in_g_tid);
+            for (int j0 = 0; j0 < in_iters; j0 += U) {
+                C v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (j0 + u < in_iters)
+                        v[u] = __ldg(src + tab.in_g[j0 + u]);
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (j0 + u < in_iters)
+                        tile[in_s_tid ^ tab.in_s[j0 + u]] = v[u];
+            }
+        }
+        __syncthreads();
+
+        // ---- the chain, in place ---------------------------------------------------------------
+        for (int sg = 0; sg < p.n_stages; sg++) {
+            const ChainStageParams &g = p.stage[sg];
+            if (g.kind == 1) {
+                ChainRegisterStage<R>(tile, Bm, p, g, tab.stage_g[sg], tid);
+            }
+            else {
+                const ChainStepParams &q = p.step[g.first];
+                constexpr bool kF = sizeof(R) == 4;
+                switch (q.log_k) {
+                case 0:
+                    ChainStep<R, 1, kF ? 4 : 2>(tile, Bm, q, tab.stage_g[sg], tid);
+                    break;
+                case 1:
+                    ChainStep<R, 2, kF ? 4 : 2>(tile, Bm, q, tab.stage_g[sg], tid);
+                    break;
+                case 2:
+                    ChainStep<R, 4, kF ? 2 : 1>(tile, Bm, q, tab.stage_g[sg], tid);
+                    break;
+                case 3:
+                    ChainStep<R, 8, kF ? 2 : 1>(tile, Bm, q, tab.stage_g[sg], tid);
+                    break;
+                default:
+                    ChainStep<R, 16, 1>(tile, Bm, q, tab.stage_g[sg], tid);
+                    break;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- store: shared memory -> X_k tile (coalesced along the low X_k address bits) ------------
+        if (out_ok) {
+            C *dst = Xk + (out_base | out_g_tid);
+            for (int j0 = 0; j0 < out_iters; j0 += U) {
+                C v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (j0 + u < out_iters)
+                        v[u] = tile[out_s_tid ^ tab.out_s[j0 + u]];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (j0 + u < out_iters)
+                        dst[tab.out_g[j0 + u]] = v[u];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename R>
+int LaunchChainT(const ChainParams &p, const ChainPtrs &ptrs, const void *x0, void *xk,
+                 cudaStream_t stream)
+{
+    using C = typename Cplx<R>::type;
+    const size_t smem = sizeof(C) * ((size_t(1) << p.log_tile) + static_cast<size_t>((p.resident_elems + 1) & ~1)) +
+                        sizeof(ChainTables);
+    auto kernel = ChainKernel<R>;
+    if (smem > 48 * 1024)
+        JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    const long long resident =
+        static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kChainThreads, smem);
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(p.n_tiles, resident)));
+    kernel<<<grid, kChainThreads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p,
+                                                  ptrs);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+// -------------------------------------------------------------------------------------------------
+// Host API
+// -------------------------------------------------------------------------------------------------
+int ChainMaxTileBits(int dtype)
+{
+    return dtype == JB_C64 ? 13 : 12; // 64 KiB of shared memory per CTA either way
+}
+
+bool ChainFusionEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_DISABLE_CHAIN");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
+}
+
+bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left)
+{
+    // the chained tensor is the larger operand; the other one must be gate-sized
+    if (cp.kernel != 0)
+        return false;
+    const int64_t size_a = cp.m * cp.k, size_b = cp.k * cp.n;
+    const bool a_big = size_a >= size_b;
+    const int64_t small = a_big ? size_b : size_a;
+    const int64_t free_small = a_big ? cp.n : cp.m;
+    if (small > 256 || cp.k > 16 || free_small > 16)
+        return false;
+    if (x_is_left)
+        *x_is_left = a_big;
+    return true;
+}
+
+int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vector<int64_t> &extent_x,
+                const std::vector<ChainOperand> &ops, int max_tile_bits, ChainOp *out,
+                std::string *why)
+{
+    std::string dummy;
+    if (why == nullptr)
+        why = &dummy;
+    std::map<std::pair<int32_t, int>, int> ids;
+    auto bits_of = [&](const std::vector<int32_t> &modes, const std::vector<int64_t> &ext,
+                       std::vector<int> *bits) {
+        bits->clear();
+        for (int i = static_cast<int>(modes.size()) - 1; i >= 0; i--) {
+            if (!IsPow2(ext[i]))
+                return false;
+            const int nb = Log2(ext[i]);
+            for (int b = 0; b < nb; b++) {
+                const auto key = std::make_pair(modes[i], b);
+                auto it = ids.find(key);
+                if (it == ids.end())
+                    it = ids.emplace(key, static_cast<int>(ids.size())).first;
+                bits->push_back(it->second);
+            }
+        }
+        return true;
+    };
+    ChainSpec spec;
+    spec.elem_bytes = static_cast<int>(ElemBytes(dtype));
+    if (!bits_of(modes_x, extent_x, &spec.x0_bits)) {
+        *why = "non power-of-two extent";
+        return 1;
+    }
+    // index-level replay for the output labels (Tensor.hpp:714-741)
+    std::vector<int32_t> cur_m = modes_x;
+    std::vector<int64_t> cur_e = extent_x;
+    double flops = 0.0, step_bytes = 0.0, r_elems = 0.0;
+    auto elems_of = [](const std::vector<int64_t> &e) {
+        double s = 1.0;
+        for (int64_t v : e)
+            s *= double(v);
+        return s;
+    };
+    const double x0_elems = elems_of(extent_x);
+    for (const ChainOperand &op : ops) {
+        ChainStepSpec st;
+        st.x_is_left = op.x_is_left;
+        if (!bits_of(op.modes, op.extent, &st.r_bits)) {
+            *why = "non power-of-two extent";
+            return 1;
+        }
+        spec.steps.push_back(st);
+        std::vector<int32_t> xm, rm;
+        std::vector<int64_t> xe, re;
+        double k = 1.0;
+        for (size_t i = 0; i < cur_m.size(); i++) {
+            const auto it = std::find(op.modes.begin(), op.modes.end(), cur_m[i]);
+            if (it == op.modes.end()) {
+                xm.push_back(cur_m[i]);
+                xe.push_back(cur_e[i]);
+            }
+            else {
+                if (op.extent[it - op.modes.begin()] != cur_e[i]) {
+                    *why = "contract: contracted extents differ between A and B";
+                    return 1;
+                }
+                k *= double(cur_e[i]);
+            }
+        }
+        for (size_t j = 0; j < op.modes.size(); j++)
+            if (std::find(cur_m.begin(), cur_m.end(), op.modes[j]) == cur_m.end()) {
+                rm.push_back(op.modes[j]);
+                re.push_back(op.extent[j]);
+            }
+        const double xin = elems_of(cur_e), rin = elems_of(op.extent);
+        if (op.x_is_left) {
+            cur_m = xm;
+            cur_e = xe;
+            cur_m.insert(cur_m.end(), rm.begin(), rm.end());
+            cur_e.insert(cur_e.end(), re.begin(), re.end());
+        }
+        else {
+            cur_m = rm;
+            cur_e = re;
+            cur_m.insert(cur_m.end(), xm.begin(), xm.end());
+            cur_e.insert(cur_e.end(), xe.begin(), xe.end());
+        }
+        const double xout = elems_of(cur_e);
+        flops += 8.0 * xout * k;
+        step_bytes += double(spec.elem_bytes) * (xin + rin + xout);
+        r_elems += rin;
+    }
+    if (static_cast<int>(cur_m.size()) > JB_MAX_RANK) {
+        *why = "contract: output rank out of range";
+        return 1;
+    }
+    ChainLayout lay;
+    const int wide = spec.elem_bytes == 8 ? 5 : 4;
+    if (!PlanChain(spec, max_tile_bits, wide, &lay, why) &&
+        !PlanChain(spec, max_tile_bits, wide - 1, &lay, why))
+        return 1;
+    // the bit-level replay must agree with the index-level one
+    {
+        std::vector<int> chk;
+        bits_of(cur_m, cur_e, &chk);
+        if (chk != lay.xk_bits) {
+            *why = "internal: chain output layout mismatch";
+            return 1;
+        }
+    }
+    out->dtype = dtype;
+    out->n_steps = static_cast<int>(ops.size());
+    out->blob.resize(sizeof(ChainParams));
+    std::memcpy(out->blob.data(), &lay.params, sizeof(ChainParams));
+    out->log_tile = lay.params.log_tile;
+    out->conflict_free = lay.conflict_free;
+    out->n_stages = lay.params.n_stages;
+    out->modes_c = cur_m;
+    out->extent_c = cur_e;
+    out->flops = flops;
+    out->step_bytes = step_bytes;
+    out->bytes = double(spec.elem_bytes) * (x0_elems + r_elems + elems_of(cur_e));
+    return 0;
+}
+
+int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk,
+                cudaStream_t stream)
+{
+    ChainParams p;
+    JB_REQUIRE(op.blob.size() == sizeof(p), "chain: not planned");
+    std::memcpy(&p, op.blob.data(), sizeof(p));
+    ChainPtrs ptrs;
+    std::memset(&ptrs, 0, sizeof(ptrs));
+    for (int s = 0; s < op.n_steps; s++)
+        ptrs.r[s] = r[s];
+    if (op.dtype == JB_C64)
+        return LaunchChainT<float>(p, ptrs, x0, xk, stream);
+    return LaunchChainT<double>(p, ptrs, x0, xk, stream);
+}
+
+} // namespace jb

@@ -113,6 +113,39 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
 int LaunchContract(const ContractPlan &plan, const void *a, const void *b, void *c, void *ws,
                    cudaStream_t stream);
 
+// ---- fused contraction chain (chain.cu) ---------------------------------------------------------
+// A run of ContractTensors calls in which each result is contracted next with a small tensor,
+// executed as ONE kernel that keeps the intermediates in shared memory.
+struct ChainOperand {
+    std::vector<int32_t> modes;
+    std::vector<int64_t> extent;
+    bool x_is_left = true; // the chained tensor is operand A of this ContractTensors call
+};
+
+struct ChainOp {
+    int dtype = JB_C64;
+    int n_steps = 0;
+    int log_tile = 0;
+    int conflict_free = 1;
+    int n_stages = 0;
+    std::vector<unsigned char> blob; // ChainParams (chain_plan.h)
+    std::vector<int32_t> modes_c;
+    std::vector<int64_t> extent_c;
+    double flops = 0.0;      // 8*M*N*K summed over the steps
+    double step_bytes = 0.0; // sizeof(T)*(MK+KN+MN) summed over the steps (unfused traffic)
+    double bytes = 0.0;      // sizeof(T)*(|X_0| + sum |R_i| + |X_k|): what the fused launch must move
+};
+
+int ChainMaxTileBits(int dtype);
+bool ChainFusionEnabled(); // false when JB_DISABLE_CHAIN=1 is set in the environment
+bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left);
+// returns non-zero (reason in *why) when the chain does not fit one tile; not an error
+int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vector<int64_t> &extent_x,
+                const std::vector<ChainOperand> &ops, int max_tile_bits, ChainOp *out,
+                std::string *why);
+int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk,
+                cudaStream_t stream);
+
 // ---- elementwise ---------------------------------------------------------------------------------
 int LaunchAdd(int dtype, int64_t n, const void *a, const void *b, void *c, cudaStream_t stream);
 int LaunchConj(int dtype, int64_t n, const void *in, void *out, cudaStream_t stream);

@@ -21,6 +21,7 @@
 #include <memory>
 #include <set>
 
+#include "chain_plan.h"
 #include "common.cuh"
 
 namespace jb {
@@ -179,6 +180,17 @@ struct Step {
     int a, b, c;
     bool shared;
     ContractPlan cp;
+    int op = -1; // per-slice launch unit executing this step
+};
+
+// A per-slice launch unit: one path step, or a fused chain of path steps (chain.cu)
+struct Op {
+    int kernel = 0; // 0 stream, 1 ttgt, 2 fused chain
+    std::vector<int> steps;
+    int x0 = -1;              // chain: node of the chained tensor before the first step
+    std::vector<int> r_nodes; // chain: small operand of every step
+    int out = -1;             // node written
+    ChainOp chain;
 };
 
 } // namespace
@@ -195,6 +207,7 @@ struct jb_plan {
     std::vector<Node> nodes;
     std::vector<Step> steps;
     std::vector<int> shared_order, slice_order;
+    std::vector<Op> ops; // per-slice launch units in execution order
     std::vector<int32_t> sliced_modes;
     std::vector<int64_t> sliced_dims;
     int64_t num_slices = 1;
@@ -222,6 +235,20 @@ struct jb_plan {
 
 namespace {
 
+int LaunchOp(jb_plan *p, const Op &op)
+{
+    if (op.kernel == 2) {
+        const void *r[kChainMaxSteps];
+        for (size_t i = 0; i < op.r_nodes.size(); i++)
+            r[i] = p->arena + p->nodes[op.r_nodes[i]].offset;
+        return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r,
+                           p->arena + p->nodes[op.out].offset, p->stream);
+    }
+    const Step &st = p->steps[op.steps[0]];
+    return LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
+                          p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream);
+}
+
 int EnqueueSliceBody(jb_plan *p)
 {
     if (!p->slice_descs.empty()) {
@@ -236,11 +263,8 @@ int EnqueueSliceBody(jb_plan *p)
                 p->At<long long>(p->list_off));
         JB_CUDA(cudaGetLastError());
     }
-    for (int s : p->slice_order) {
-        const Step &st = p->steps[s];
-        JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
-                              p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream));
-    }
+    for (const Op &op : p->ops)
+        JB_TRY(LaunchOp(p, op));
     const bool store = (p->flags & JB_PLAN_STORE_RESULTS) != 0;
     const void *res = p->arena + p->nodes[p->result_node].offset;
     if (p->dtype == JB_C64)
@@ -458,16 +482,116 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     for (size_t s = 0; s < p->steps.size(); s++)
         (p->steps[s].shared ? p->shared_order : p->slice_order).push_back(static_cast<int>(s));
 
-    // ---- lifetimes in execution order (shared steps first, then per-slice steps) ------------------
-    std::vector<int> exec = p->shared_order;
-    exec.insert(exec.end(), p->slice_order.begin(), p->slice_order.end());
+    // ---- per-slice launch units: fuse runs of "large tensor absorbs a small tensor" steps ----------
+    {
+        const bool fuse = !keep && !(d->flags & JB_PLAN_NO_FUSE) && ChainFusionEnabled();
+        std::vector<int> consumer(p->nodes.size(), -1);
+        for (size_t s = 0; s < p->steps.size(); s++) {
+            consumer[p->steps[s].a] = static_cast<int>(s);
+            consumer[p->steps[s].b] = static_cast<int>(s);
+        }
+        // a step can join a chain whose running tensor is node x when its other operand is small
+        auto as_operand = [&](int s, int x, ChainOperand *o, int *r_node) {
+            const Step &st = p->steps[s];
+            if (st.shared || st.cp.kernel != 0)
+                return false;
+            const bool x_left = st.a == x;
+            const int r = x_left ? st.b : st.a;
+            const int64_t free_r = x_left ? st.cp.n : st.cp.m;
+            if (st.cp.k > 16 || free_r > 16)
+                return false;
+            o->modes = p->nodes[r].modes;
+            o->extent = p->nodes[r].extent;
+            o->x_is_left = x_left;
+            *r_node = r;
+            return true;
+        };
+        std::vector<char> taken(p->steps.size(), 0);
+        std::vector<Op> ops;
+        const int max_tile = ChainMaxTileBits(p->dtype);
+        for (int s : p->slice_order) {
+            if (taken[s])
+                continue;
+            const Step &st = p->steps[s];
+            Op single;
+            single.kernel = st.cp.kernel;
+            single.steps = {s};
+            single.out = st.c;
+            if (!fuse) {
+                ops.push_back(single);
+                continue;
+            }
+            const int x0 = (p->nodes[st.a].elems >= p->nodes[st.b].elems) ? st.a : st.b;
+            Op chain;
+            chain.kernel = 2;
+            chain.x0 = x0;
+            std::vector<ChainOperand> operands;
+            int x = x0, cur = s;
+            while (cur >= 0 && !taken[cur] && static_cast<int>(operands.size()) < kChainMaxSteps) {
+                ChainOperand o;
+                int r_node = -1;
+                if (!as_operand(cur, x, &o, &r_node))
+                    break;
+                operands.push_back(o);
+                ChainOp trial;
+                if (MakeChainOp(p->dtype, p->nodes[x0].modes, p->nodes[x0].extent, operands, max_tile,
+                                &trial, nullptr) != 0) {
+                    operands.pop_back();
+                    break;
+                }
+                chain.chain = trial;
+                chain.steps.push_back(cur);
+                chain.r_nodes.push_back(r_node);
+                chain.out = p->steps[cur].c;
+                x = p->steps[cur].c;
+                cur = consumer[x];
+            }
+            if (chain.steps.size() >= 2) {
+                for (int cs : chain.steps)
+                    taken[cs] = 1;
+                ops.push_back(chain);
+            }
+            else {
+                taken[s] = 1;
+                ops.push_back(single);
+            }
+        }
+        // a unit runs where its LAST step stood in the path: everything it reads exists by then
+        std::stable_sort(ops.begin(), ops.end(),
+                         [](const Op &x, const Op &y) { return x.steps.back() < y.steps.back(); });
+        p->ops = ops;
+        for (size_t o = 0; o < p->ops.size(); o++)
+            for (int cs : p->ops[o].steps)
+                p->steps[cs].op = static_cast<int>(o);
+    }
+
+    // ---- lifetimes in execution order (shared steps first, then per-slice launch units) -----------
+    struct Exec {
+        std::vector<int> reads;
+        int out;
+        bool shared;
+    };
+    std::vector<Exec> exec;
+    for (int s : p->shared_order)
+        exec.push_back({{p->steps[s].a, p->steps[s].b}, p->steps[s].c, true});
+    for (const Op &op : p->ops) {
+        Exec e;
+        e.shared = false;
+        e.out = op.out;
+        if (op.kernel == 2) {
+            e.reads = op.r_nodes;
+            e.reads.push_back(op.x0);
+        }
+        else {
+            e.reads = {p->steps[op.steps[0]].a, p->steps[op.steps[0]].b};
+        }
+        exec.push_back(e);
+    }
     for (size_t e = 0; e < exec.size(); e++) {
-        const Step &st = p->steps[exec[e]];
-        p->nodes[st.a].last_use = static_cast<int>(e);
-        p->nodes[st.b].last_use = static_cast<int>(e);
-        if (!st.shared) {
-            p->nodes[st.a].used_by_slice_step = true;
-            p->nodes[st.b].used_by_slice_step = true;
+        for (int in : exec[e].reads) {
+            p->nodes[in].last_use = static_cast<int>(e);
+            if (!exec[e].shared)
+                p->nodes[in].used_by_slice_step = true;
         }
     }
     // fixed regions first (never recycled): workspace, accumulator, per-slice result store, state,
@@ -488,14 +612,14 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
     p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
     for (size_t e = 0; e < exec.size(); e++) {
-        const Step &st = p->steps[exec[e]];
-        Node &C = p->nodes[st.c];
+        Node &C = p->nodes[exec[e].out];
         C.offset = alloc.Alloc(C.elems * p->eb);
         if (keep)
             continue;
-        for (int in : {st.a, st.b}) {
+        std::set<int> seen;
+        for (int in : exec[e].reads) {
             Node &I = p->nodes[in];
-            if (I.is_leaf || I.last_use != static_cast<int>(e))
+            if (I.is_leaf || I.last_use != static_cast<int>(e) || !seen.insert(in).second)
                 continue;
             // a shared tensor read by per-slice steps must survive every slice
             const bool producer_shared = !I.slice_dep;
@@ -550,7 +674,19 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         else {
             S.flops_per_slice += st.cp.flops();
             S.bytes_per_slice += st.cp.bytes();
+        }
+    }
+    for (const Op &op : p->ops) {
+        if (op.kernel == 2) {
+            S.chains++;
+            S.steps_chained += static_cast<int32_t>(op.steps.size());
+            S.launches_per_slice += 1;
+            S.fused_bytes_per_slice += op.chain.bytes;
+        }
+        else {
+            const Step &st = p->steps[op.steps[0]];
             S.launches_per_slice += st.cp.launches;
+            S.fused_bytes_per_slice += st.cp.bytes();
             if (st.cp.kernel == 0)
                 S.steps_stream++;
             else
@@ -743,11 +879,44 @@ int jb_plan_steps(const jb_plan *p, jb_step_info_t *steps, int32_t cap, int32_t 
         o.k = st.cp.k;
         o.flops = st.cp.flops();
         o.bytes = st.cp.bytes();
+        o.op = st.op;
+        o.pad = 0;
     }
     return 0;
 }
 
-int jb_plan_profile(jb_plan *p, int64_t slice, int reps, float *ms, int32_t cap)
+int jb_plan_ops(const jb_plan *p, jb_op_info_t *ops, int32_t cap, int32_t *count)
+{
+    JB_REQUIRE(p && count, "plan: null argument");
+    *count = static_cast<int32_t>(p->ops.size());
+    for (int32_t i = 0; i < std::min<int32_t>(cap, *count); i++) {
+        const Op &op = p->ops[i];
+        jb_op_info_t &o = ops[i];
+        o.kernel = op.kernel;
+        o.n_steps = static_cast<int32_t>(op.steps.size());
+        o.first_step = op.steps.front();
+        o.last_step = op.steps.back();
+        o.log_tile = op.kernel == 2 ? op.chain.log_tile : 0;
+        o.n_stages = op.kernel == 2 ? op.chain.n_stages : 0;
+        o.pad = 0;
+        o.flops = o.bytes = o.step_bytes = 0.0;
+        if (op.kernel == 2) {
+            o.launches = 1;
+            o.flops = op.chain.flops;
+            o.bytes = op.chain.bytes;
+            o.step_bytes = op.chain.step_bytes;
+        }
+        else {
+            const Step &st = p->steps[op.steps[0]];
+            o.launches = st.cp.launches;
+            o.flops = st.cp.flops();
+            o.bytes = o.step_bytes = st.cp.bytes();
+        }
+    }
+    return 0;
+}
+
+int jb_plan_profile_ops(jb_plan *p, int64_t slice, int reps, float *ms, int32_t cap)
 {
     JB_REQUIRE(p && ms, "plan: null argument");
     JB_REQUIRE(slice >= 0 && slice < p->num_slices, "plan: slice id out of bounds");
@@ -756,11 +925,11 @@ int jb_plan_profile(jb_plan *p, int64_t slice, int reps, float *ms, int32_t cap)
     for (int32_t i = 0; i < cap; i++)
         ms[i] = 0.f;
     // one eager pass leaves every per-slice input in place (lifetimes are respected because the
-    // steps are replayed in plan order)
-    std::vector<cudaEvent_t> ev(p->slice_order.size() + 1);
+    // units are replayed in plan order)
+    std::vector<cudaEvent_t> ev(p->ops.size() + 1);
     for (auto &e : ev)
         JB_CUDA(cudaEventCreate(&e));
-    std::vector<double> total(p->slice_order.size(), 0.0);
+    std::vector<double> total(p->ops.size(), 0.0);
     for (int r = 0; r < reps + 1; r++) {
         SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), slice, -1, 0);
         if (!p->slice_descs.empty()) {
@@ -774,30 +943,41 @@ int jb_plan_profile(jb_plan *p, int64_t slice, int reps, float *ms, int32_t cap)
                     p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off),
                     p->At<DeviceState>(p->state_off), p->At<long long>(p->list_off));
         }
-        for (size_t i = 0; i < p->slice_order.size(); i++) {
-            const Step &st = p->steps[p->slice_order[i]];
+        for (size_t i = 0; i < p->ops.size(); i++) {
             JB_CUDA(cudaEventRecord(ev[i], p->stream));
-            JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset,
-                                  p->arena + p->nodes[st.b].offset, p->arena + p->nodes[st.c].offset,
-                                  p->arena + p->ws_off, p->stream));
+            JB_TRY(LaunchOp(p, p->ops[i]));
         }
         JB_CUDA(cudaEventRecord(ev.back(), p->stream));
         JB_CUDA(cudaStreamSynchronize(p->stream));
         if (r == 0)
             continue; // warm-up
-        for (size_t i = 0; i < p->slice_order.size(); i++) {
+        for (size_t i = 0; i < p->ops.size(); i++) {
             float t = 0.f;
             JB_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
             total[i] += t;
         }
     }
-    for (size_t i = 0; i < p->slice_order.size(); i++) {
-        const int s = p->slice_order[i];
-        if (s < cap)
-            ms[s] = static_cast<float>(total[i] / std::max(reps, 1));
-    }
+    for (size_t i = 0; i < p->ops.size(); i++)
+        if (static_cast<int32_t>(i) < cap)
+            ms[i] = static_cast<float>(total[i] / std::max(reps, 1));
     for (auto &e : ev)
         cudaEventDestroy(e);
+    return 0;
+}
+
+int jb_plan_profile(jb_plan *p, int64_t slice, int reps, float *ms, int32_t cap)
+{
+    JB_REQUIRE(p && ms, "plan: null argument");
+    std::vector<float> per_op(p->ops.size() + 1, 0.f);
+    JB_TRY(jb_plan_profile_ops(p, slice, reps, per_op.data(), static_cast<int32_t>(p->ops.size())));
+    for (int32_t i = 0; i < cap; i++)
+        ms[i] = 0.f;
+    // a fused chain's time is attributed to its last step
+    for (size_t i = 0; i < p->ops.size(); i++) {
+        const int s = p->ops[i].steps.back();
+        if (s < cap)
+            ms[s] = per_op[i];
+    }
     return 0;
 }
 

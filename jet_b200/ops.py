@@ -13,7 +13,7 @@ from typing import Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import JB_C64, JB_C128, ContractInfo, check, lib
+from ._lib import JB_C64, JB_C128, ChainDesc, ChainInfo, ContractInfo, check, lib
 
 
 def dtype_code(dtype) -> int:
@@ -68,6 +68,42 @@ def contract(a: np.ndarray, modes_a: Sequence[int], b: np.ndarray, modes_b: Sequ
     out = np.empty(int(info.m * info.n), dtype=a.dtype)
     check(lib().jb_contract_host(dtype_code(a.dtype), a.ndim, _i64(a.shape), _i32(modes_a), _ptr(a), b.ndim,
                                  _i64(b.shape), _i32(modes_b), _ptr(b), _ptr(out)))
+    return out.reshape(shape_c), [info.modes_c[i] for i in range(info.rank_c)]
+
+
+def _chain_desc(dtype, shape_x, modes_x, operands):
+    """operands: list of (shape_r, modes_r, x_is_left)."""
+    n = len(operands)
+    keep = dict(
+        ex=_i64(shape_x), mx=_i32(modes_x), rr=_i32([len(o[0]) for o in operands]),
+        er=_i64([v for o in operands for v in o[0]]), mr=_i32([v for o in operands for v in o[1]]),
+        xl=_i32([1 if o[2] else 0 for o in operands]))
+    desc = ChainDesc(dtype_code(dtype), n, len(shape_x), keep["ex"], keep["mx"], keep["rr"], keep["er"], keep["mr"],
+                     keep["xl"])
+    return desc, keep
+
+
+def chain_info(dtype, shape_x, modes_x, operands) -> ChainInfo:
+    desc, _keep = _chain_desc(dtype, shape_x, modes_x, operands)
+    info = ChainInfo()
+    check(lib().jb_chain_info(C.byref(desc), C.byref(info)))
+    return info
+
+
+def contract_chain(x: np.ndarray, modes_x: Sequence[int], operands) -> Tuple[np.ndarray, list]:
+    """A run of ContractTensors calls as ONE fused launch.  operands: list of (r, modes_r, x_is_left);
+    step i computes ContractTensors(X, r) if x_is_left else ContractTensors(r, X) (Tensor.hpp:709-752)
+    and feeds the result to step i+1.  Returns (X_k, modes of X_k)."""
+    x = np.ascontiguousarray(x)
+    rs = [np.ascontiguousarray(r, dtype=x.dtype) for r, _, _ in operands]
+    spec = [(list(r.shape), list(m), bool(left)) for r, (_, m, left) in zip(rs, operands)]
+    desc, _keep = _chain_desc(x.dtype, x.shape, modes_x, spec)
+    info = ChainInfo()
+    check(lib().jb_chain_info(C.byref(desc), C.byref(info)))
+    shape_c = [info.extent_c[i] for i in range(info.rank_c)]
+    out = np.empty(int(np.prod(shape_c, dtype=np.int64)) if shape_c else 1, dtype=x.dtype)
+    rp = (C.c_void_p * len(rs))(*[r.ctypes.data for r in rs])
+    check(lib().jb_contract_chain_host(C.byref(desc), _ptr(x), rp, _ptr(out)))
     return out.reshape(shape_c), [info.modes_c[i] for i in range(info.rank_c)]
 
 

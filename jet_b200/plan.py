@@ -14,8 +14,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import (JB_PLAN_KEEP_INTERMEDIATES, JB_PLAN_NO_GRAPH, JB_PLAN_STORE_RESULTS, NetworkDesc, PlanStats,
-                   StepInfo, check, lib)
+from ._lib import (JB_PLAN_KEEP_INTERMEDIATES, JB_PLAN_NO_FUSE, JB_PLAN_NO_GRAPH, JB_PLAN_STORE_RESULTS, NetworkDesc,
+                   OpInfo, PlanStats, StepInfo, check, lib)
 from .ops import dtype_code
 
 
@@ -85,7 +85,8 @@ class ContractionPlan:
     """A sliced network + path resident on one GPU (wraps jb_plan)."""
 
     def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), device: int = 0, keep_intermediates=False,
-                 use_graph=True, store_results=False, path: Optional[Sequence[Sequence[int]]] = None):
+                 use_graph=True, store_results=False, path: Optional[Sequence[Sequence[int]]] = None,
+                 fuse=True):
         self.net = net
         self.sliced = list(sliced)
         self.device = device
@@ -113,7 +114,7 @@ class ContractionPlan:
         self._path = (C.c_int32 * max(len(flat_path), 1))(*flat_path)
         self._sliced = (C.c_int32 * max(len(self.sliced), 1))(*[labels[s] for s in self.sliced])
         flags = (JB_PLAN_KEEP_INTERMEDIATES if keep_intermediates else 0) | (0 if use_graph else JB_PLAN_NO_GRAPH) | (
-            JB_PLAN_STORE_RESULTS if store_results else 0)
+            JB_PLAN_STORE_RESULTS if store_results else 0) | (0 if fuse else JB_PLAN_NO_FUSE)
         desc = NetworkDesc(dtype_code(self.dtype), device, n, self._rank, self._extent, self._mode, self._data,
                            len(steps), self._path, len(self.sliced), self._sliced, flags)
         self._h = C.c_void_p()
@@ -210,6 +211,20 @@ class ContractionPlan:
         n = len(self.steps())
         ms = np.zeros(max(n, 1), dtype=np.float32)
         check(lib().jb_plan_profile(self._h, slice_id, reps, ms.ctypes.data_as(C.c_void_p), n))
+        return ms[:n]
+
+    def ops(self) -> List[OpInfo]:
+        """Launch units of one slice in execution order (single steps and fused chains)."""
+        n = C.c_int32()
+        check(lib().jb_plan_ops(self._h, None, 0, C.byref(n)))
+        arr = (OpInfo * max(n.value, 1))()
+        check(lib().jb_plan_ops(self._h, arr, n.value, C.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def profile_ops(self, slice_id: int = 0, reps: int = 3) -> np.ndarray:
+        n = len(self.ops())
+        ms = np.zeros(max(n, 1), dtype=np.float32)
+        check(lib().jb_plan_profile_ops(self._h, slice_id, reps, ms.ctypes.data_as(C.c_void_p), n))
         return ms[:n]
 
     def amplitude(self, slice_ids: Optional[Sequence[int]] = None) -> np.ndarray:
