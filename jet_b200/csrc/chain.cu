@@ -24,10 +24,12 @@ struct ChainPtrs {
     const void *r[kChainMaxSteps];
 };
 
+static_assert(sizeof(ChainParams) + sizeof(ChainPtrs) <= 4000, "kernel parameter space is 4 KB");
+
 namespace {
 
-constexpr int kChainThreads = 256;
-constexpr int kLogChainThreads = 8;
+constexpr int kLogChainThreads = kChainLogThreads;
+constexpr int kChainThreads = 1 << kLogChainThreads;
 
 template <typename R> struct Cplx;
 template <> struct Cplx<float> {
@@ -70,7 +72,7 @@ template <typename R, int KC, int G>
 __device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ tile,
                                           const typename Cplx<R>::type *__restrict__ Bm,
                                           const ChainStepParams &q,
-                                          const unsigned *__restrict__ gtab, const int tid)
+                                          const uint16_t *__restrict__ gtab, const int tid)
 {
     using C = typename Cplx<R>::type;
     const int log_g = q.log_g;
@@ -184,26 +186,39 @@ __device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
     constexpr int LK = ((MASK >> 0) & 1) + ((MASK >> 1) & 1) + ((MASK >> 2) & 1) + ((MASK >> 3) & 1);
     constexpr int K = 1 << LK;
     constexpr int NE = 1 << NL;
-    C out[NE];
+    // group by group, in place: the K inputs of a group are replaced by its K outputs
 #pragma unroll
-    for (int e = 0; e < NE; e++)
-        out[e] = C{R(0), R(0)};
+    for (int g = 0; g < NE; g++) {
+        if (g & MASK)
+            continue;
+        C acc[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) {
+        for (int n = 0; n < K; n++)
+            acc[n] = C{R(0), R(0)};
 #pragma unroll
-        for (int n = 0; n < K; n++) {
-            const C r = B[k * np + n];
+        for (int k = 0; k < K; k++) {
+            const C a = E[g | Spread<MASK>(k)];
 #pragma unroll
-            for (int g = 0; g < NE; g++) {
-                if (g & MASK)
-                    continue;
-                CMulAdd(out[g | Spread<MASK>(n)], E[g | Spread<MASK>(k)], r);
+            for (int n0 = 0; n0 < K; n0 += 2) {
+                // two matrix entries per shared-memory load (rows are 32-byte aligned: np % 4 == 0)
+                C r[2];
+                if constexpr (sizeof(C) == 8) {
+                    const float4 v = *reinterpret_cast<const float4 *>(B + k * np + n0);
+                    r[0] = C{v.x, v.y};
+                    r[1] = C{v.z, v.w};
+                }
+                else {
+                    r[0] = B[k * np + n0];
+                    r[1] = B[k * np + n0 + 1];
+                }
+                CMulAdd(acc[n0], a, r[0]);
+                CMulAdd(acc[n0 + 1], a, r[1]);
             }
         }
-    }
 #pragma unroll
-    for (int e = 0; e < NE; e++)
-        E[e] = out[e];
+        for (int n = 0; n < K; n++)
+            E[g | Spread<MASK>(n)] = acc[n];
+    }
 }
 
 template <typename R, int NL>
@@ -247,7 +262,7 @@ template <typename R>
 __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__restrict__ tile,
                                                    const typename Cplx<R>::type *__restrict__ Bm,
                                                    const ChainParams &p, const ChainStageParams &g,
-                                                   const unsigned *__restrict__ gtab, const int tid)
+                                                   const uint16_t *__restrict__ gtab, const int tid)
 {
     using C = typename Cplx<R>::type;
     constexpr int NL = sizeof(R) == 4 ? 4 : 3;
@@ -283,15 +298,8 @@ __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__res
     }
 }
 
-// shared-memory tables of the thread-independent parts of the index maps (built once per CTA)
-struct ChainTables {
-    unsigned long long in_g[32], out_g[32];
-    unsigned in_s[32], out_s[32];
-    unsigned stage_g[kChainMaxSteps][32];
-};
-
-template <typename R>
-__global__ void __launch_bounds__(kChainThreads, 2)
+template <typename R, int MINB>
+__global__ void __launch_bounds__(kChainThreads, MINB)
     ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
                 typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
                 const __grid_constant__ ChainPtrs rp)
@@ -300,7 +308,6 @@ __global__ void __launch_bounds__(kChainThreads, 2)
     extern __shared__ __align__(16) unsigned char chain_smem[];
     C *tile = reinterpret_cast<C *>(chain_smem);
     C *Bm = tile + (1 << p.log_tile);
-    ChainTables &tab = *reinterpret_cast<ChainTables *>(Bm + ((p.resident_elems + 1) & ~1));
     const int tid = threadIdx.x;
 
     // resident operands -> shared memory as K x np matrices (columns n >= N are zero)
@@ -321,27 +328,6 @@ __global__ void __launch_bounds__(kChainThreads, 2)
 
     const int in_tid_bits = min(p.log_tile_in, kLogChainThreads);
     const int out_tid_bits = min(p.log_tile_out, kLogChainThreads);
-    if (tid < 32) {
-        tab.in_g[tid] = Deposit(tid, p.in_gbit + kLogChainThreads, p.log_tile_in - in_tid_bits);
-        tab.in_s[tid] = Lin(tid, p.in_scol + kLogChainThreads, p.log_tile_in - in_tid_bits);
-        tab.out_g[tid] = Deposit(tid, p.out_gbit + kLogChainThreads, p.log_tile_out - out_tid_bits);
-        tab.out_s[tid] = Lin(tid, p.out_scol + kLogChainThreads, p.log_tile_out - out_tid_bits);
-    }
-    for (int e = tid; e < p.n_stages * 32; e += kChainThreads) {
-        const int st = e >> 5, j = e & 31;
-        const ChainStageParams &g = p.stage[st];
-        unsigned v;
-        if (g.kind == 1) {
-            const int tb = min(static_cast<int>(g.log_g), kLogChainThreads);
-            v = Lin(j, g.gcol + kLogChainThreads, g.log_g - tb);
-        }
-        else {
-            const ChainStepParams &q = p.step[g.first];
-            const int tb = min(static_cast<int>(q.log_g), kLogChainThreads);
-            v = Lin(j, q.gcol + kLogChainThreads, q.log_g - tb);
-        }
-        tab.stage_g[st][j] = v;
-    }
 
     // per-thread parts of the load / store index maps (tile independent)
     const unsigned in_s_tid = Lin(tid, p.in_scol, in_tid_bits);
@@ -360,46 +346,47 @@ __global__ void __launch_bounds__(kChainThreads, 2)
         const unsigned long long out_base = Deposit(static_cast<unsigned long long>(t), p.outer_out, p.log_outer);
 
         // ---- load: X_0 tile -> shared memory (coalesced along the low X_0 address bits) ----------
+        // cp.async: every element of the tile is in flight at once and no register is staged
         if (in_ok) {
             const C *src = X0 + (in_base | in_g_tid);
-            for (int j0 = 0; j0 < in_iters; j0 += U) {
-                C v[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (j0 + u < in_iters)
-                        v[u] = __ldg(src + tab.in_g[j0 + u]);
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (j0 + u < in_iters)
-                        tile[in_s_tid ^ tab.in_s[j0 + u]] = v[u];
+            const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
+#pragma unroll 8
+            for (int j = 0; j < in_iters; j++) {
+                const unsigned dst = tile_s + (in_s_tid ^ p.in_stab[j]) * static_cast<unsigned>(sizeof(C));
+                const C *g = src + p.in_gtab[j];
+                if constexpr (sizeof(C) == 8)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
+                else
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 
         // ---- the chain, in place ---------------------------------------------------------------
         for (int sg = 0; sg < p.n_stages; sg++) {
             const ChainStageParams &g = p.stage[sg];
             if (g.kind == 1) {
-                ChainRegisterStage<R>(tile, Bm, p, g, tab.stage_g[sg], tid);
+                ChainRegisterStage<R>(tile, Bm, p, g, p.stage_tab[sg], tid);
             }
             else {
                 const ChainStepParams &q = p.step[g.first];
                 constexpr bool kF = sizeof(R) == 4;
                 switch (q.log_k) {
                 case 0:
-                    ChainStep<R, 1, kF ? 4 : 2>(tile, Bm, q, tab.stage_g[sg], tid);
+                    ChainStep<R, 1, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], tid);
                     break;
                 case 1:
-                    ChainStep<R, 2, kF ? 4 : 2>(tile, Bm, q, tab.stage_g[sg], tid);
+                    ChainStep<R, 2, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], tid);
                     break;
                 case 2:
-                    ChainStep<R, 4, kF ? 2 : 1>(tile, Bm, q, tab.stage_g[sg], tid);
+                    ChainStep<R, 4, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], tid);
                     break;
                 case 3:
-                    ChainStep<R, 8, kF ? 2 : 1>(tile, Bm, q, tab.stage_g[sg], tid);
+                    ChainStep<R, 8, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], tid);
                     break;
                 default:
-                    ChainStep<R, 16, 1>(tile, Bm, q, tab.stage_g[sg], tid);
+                    ChainStep<R, 16, 1>(tile, Bm, q, p.stage_tab[sg], tid);
                     break;
                 }
             }
@@ -414,25 +401,24 @@ __global__ void __launch_bounds__(kChainThreads, 2)
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (j0 + u < out_iters)
-                        v[u] = tile[out_s_tid ^ tab.out_s[j0 + u]];
+                        v[u] = tile[out_s_tid ^ p.out_stab[j0 + u]];
 #pragma unroll
                 for (int u = 0; u < U; u++)
                     if (j0 + u < out_iters)
-                        dst[tab.out_g[j0 + u]] = v[u];
+                        dst[p.out_gtab[j0 + u]] = v[u];
             }
         }
         __syncthreads();
     }
 }
 
-template <typename R>
+template <typename R, int MINB>
 int LaunchChainT(const ChainParams &p, const ChainPtrs &ptrs, const void *x0, void *xk,
                  cudaStream_t stream)
 {
     using C = typename Cplx<R>::type;
-    const size_t smem = sizeof(C) * ((size_t(1) << p.log_tile) + static_cast<size_t>((p.resident_elems + 1) & ~1)) +
-                        sizeof(ChainTables);
-    auto kernel = ChainKernel<R>;
+    const size_t smem = sizeof(C) * ((size_t(1) << p.log_tile) + static_cast<size_t>(p.resident_elems));
+    auto kernel = ChainKernel<R, MINB>;
     if (smem > 48 * 1024)
         JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
@@ -613,9 +599,14 @@ int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *x
     std::memset(&ptrs, 0, sizeof(ptrs));
     for (int s = 0; s < op.n_steps; s++)
         ptrs.r[s] = r[s];
+    static const int minb = [] {
+        const char *e = getenv("JB_CHAIN_MINB");
+        return e ? atoi(e) : 2;
+    }();
     if (op.dtype == JB_C64)
-        return LaunchChainT<float>(p, ptrs, x0, xk, stream);
-    return LaunchChainT<double>(p, ptrs, x0, xk, stream);
+        return minb == 3 ? LaunchChainT<float, 3>(p, ptrs, x0, xk, stream)
+                         : LaunchChainT<float, 2>(p, ptrs, x0, xk, stream);
+    return LaunchChainT<double, 2>(p, ptrs, x0, xk, stream);
 }
 
 } // namespace jb

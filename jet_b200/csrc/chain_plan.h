@@ -31,6 +31,8 @@ constexpr int kChainMaxTileBits = 13;
 constexpr int kChainMaxOuterBits = 56;
 constexpr int kChainMaxLogK = 4;
 constexpr int kChainMaxLogN = 4;
+constexpr int kChainLogThreads = 8; // the kernel runs 256-thread CTAs
+constexpr int kChainTabLen = 1 << (kChainMaxTileBits - kChainLogThreads);
 
 struct ChainStepParams {
     uint8_t log_k, log_n, log_g, pad0;
@@ -75,6 +77,11 @@ struct ChainParams {
     uint8_t outer_out[kChainMaxOuterBits]; // X_k address bit of tile-number bit q
     ChainStepParams step[kChainMaxSteps];
     ChainStageParams stage[kChainMaxSteps];
+    // thread-independent parts of the index maps, tabulated for 256-thread CTAs: entry j is the
+    // contribution of work-index bits 8.. (j = index >> 8)
+    unsigned long long in_gtab[kChainTabLen], out_gtab[kChainTabLen];
+    uint16_t in_stab[kChainTabLen], out_stab[kChainTabLen];
+    uint16_t stage_tab[kChainMaxSteps][kChainTabLen];
 };
 
 struct ChainStepSpec {
@@ -455,6 +462,36 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
     for (size_t q = 0; q < outer.size(); q++) {
         P.outer_in[q] = static_cast<uint8_t>(addr0[outer[q]]);
         P.outer_out[q] = static_cast<uint8_t>(addrk[outer[q]]);
+    }
+    // ---- tables ---------------------------------------------------------------------------------
+    {
+        auto lin = [](unsigned idx, const uint16_t *c, int nbits) {
+            unsigned r = 0;
+            for (int q = 0; q < nbits; q++)
+                if ((idx >> q) & 1u)
+                    r ^= c[q];
+            return r;
+        };
+        auto dep = [](unsigned idx, const uint8_t *bit, int nbits) {
+            unsigned long long r = 0;
+            for (int q = 0; q < nbits; q++)
+                r |= static_cast<unsigned long long>((idx >> q) & 1u) << bit[q];
+            return r;
+        };
+        const int L = kChainLogThreads;
+        for (int j = 0; j < kChainTabLen; j++) {
+            const int ib = std::max(0, P.log_tile_in - L), ob = std::max(0, P.log_tile_out - L);
+            P.in_gtab[j] = dep(j, P.in_gbit + L, ib);
+            P.in_stab[j] = static_cast<uint16_t>(lin(j, P.in_scol + L, ib));
+            P.out_gtab[j] = dep(j, P.out_gbit + L, ob);
+            P.out_stab[j] = static_cast<uint16_t>(lin(j, P.out_scol + L, ob));
+            for (int sg = 0; sg < P.n_stages; sg++) {
+                const ChainStageParams &G = P.stage[sg];
+                const uint16_t *gc = G.kind == 1 ? G.gcol : P.step[G.first].gcol;
+                const int lg = G.kind == 1 ? G.log_g : P.step[G.first].log_g;
+                P.stage_tab[sg][j] = static_cast<uint16_t>(lin(j, gc + L, std::max(0, lg - L)));
+            }
+        }
     }
     out->xk_bits = xk;
     return true;

@@ -105,9 +105,9 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                     if (tid >= (1 << p.log_tile_in))
                         continue;
                     const unsigned long long g = in_base | ChainDeposit(tid, p.in_gbit, in_tid_bits) |
-                                                 ChainDeposit(j, p.in_gbit + kLogThreads, p.log_tile_in - in_tid_bits);
+                                                 p.in_gtab[j];
                     const unsigned sa = ChainLin(tid, p.in_scol, in_tid_bits) ^
-                                        ChainLin(j, p.in_scol + kLogThreads, p.log_tile_in - in_tid_bits);
+                                        p.in_stab[j];
                     tile[sa] = cd(x0[2 * g], x0[2 * g + 1]);
                     lanes[l] = sa;
                 }
@@ -134,7 +134,7 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                             if (tid >= (1 << log_g))
                                 continue;
                             const unsigned base = ChainLin(tid, G.gcol, tid_bits) ^
-                                                  ChainLin(j, G.gcol + kLogThreads, log_g - tid_bits);
+                                                  p.stage_tab[sg][j];
                             std::vector<cd> E(NE);
                             std::vector<unsigned> ad(NE);
                             for (int e = 0; e < NE; e++) {
@@ -200,7 +200,7 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                         if (tid >= (1 << log_g))
                             continue;
                         const unsigned base = ChainLin(tid, q.gcol, tid_bits) ^
-                                              ChainLin(j, q.gcol + kLogThreads, log_g - tid_bits);
+                                              p.stage_tab[sg][j];
                         std::vector<cd> a(K);
                         for (int kk = 0; kk < K; kk++) {
                             const unsigned ad = base ^ ChainLin(kk, q.kcol, q.log_k);
@@ -245,9 +245,9 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                     if (tid >= (1 << p.log_tile_out))
                         continue;
                     const unsigned long long g = out_base | ChainDeposit(tid, p.out_gbit, out_tid_bits) |
-                                                 ChainDeposit(j, p.out_gbit + kLogThreads, p.log_tile_out - out_tid_bits);
+                                                 p.out_gtab[j];
                     const unsigned sa = ChainLin(tid, p.out_scol, out_tid_bits) ^
-                                        ChainLin(j, p.out_scol + kLogThreads, p.log_tile_out - out_tid_bits);
+                                        p.out_stab[j];
                     out[2 * g] = tile[sa].real();
                     out[2 * g + 1] = tile[sa].imag();
                     lanes[l] = sa;
