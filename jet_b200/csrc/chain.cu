@@ -47,6 +47,30 @@ template <typename C> __device__ __forceinline__ void CMulAdd(C &acc, const C a,
     acc.y = fma(a.y, b.x, acc.y);
 }
 
+// Packed FP32 pair arithmetic (sm_100a FFMA2): one instruction issues two IEEE FMAs, so a complex
+// multiply-add is 2 issue slots instead of 4 — the FMA pipe, not the scheduler, becomes the limit.
+__device__ __forceinline__ unsigned long long Pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 Unpack2(unsigned long long v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// acc += a * b for complex a, b with b given as (b.x, b.y, -b.y, b.x): same two FMAs per component,
+// in the same order, as CMulAdd
+__device__ __forceinline__ void CMulAdd2(unsigned long long &acc, const float2 a, const float4 bb)
+{
+    const unsigned long long ax = Pack2(a.x, a.x), ay = Pack2(a.y, a.y);
+    const unsigned long long b0 = Pack2(bb.x, bb.y), b1 = Pack2(bb.z, bb.w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ax), "l"(b0));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ay), "l"(b1));
+}
+
 __device__ __forceinline__ unsigned Lin(unsigned idx, const uint16_t *col, int nbits)
 {
     unsigned r = 0;
@@ -177,90 +201,106 @@ template <int MASK> __device__ __forceinline__ constexpr int Spread(int v)
     return r;
 }
 
+// The matrix of a register-stage step: complex64 entries are stored as (b.x, b.y, -b.y, b.x) so that
+// both packed FMAs of a complex multiply-add read their operand from one 16-byte load.
+template <typename R> struct StageB;
+template <> struct StageB<float> {
+    using type = float4;
+};
+template <> struct StageB<double> {
+    using type = double2;
+};
+
 // NL local bits: 4 for complex64 (16 elements = 32 registers), 3 for complex128.
 template <typename R, int NL, int MASK>
 __device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
-                                           const typename Cplx<R>::type *__restrict__ B, const int np)
+                                           const typename StageB<R>::type *__restrict__ B)
 {
     using C = typename Cplx<R>::type;
     constexpr int LK = ((MASK >> 0) & 1) + ((MASK >> 1) & 1) + ((MASK >> 2) & 1) + ((MASK >> 3) & 1);
     constexpr int K = 1 << LK;
     constexpr int NE = 1 << NL;
+    constexpr int NP = K < 4 ? 4 : K; // row stride of the matrix: ChainStepParams::np for K == N
     // group by group, in place: the K inputs of a group are replaced by its K outputs
 #pragma unroll
     for (int g = 0; g < NE; g++) {
         if (g & MASK)
             continue;
-        C acc[K];
+        if constexpr (sizeof(R) == 4) {
+            unsigned long long acc[K];
 #pragma unroll
-        for (int n = 0; n < K; n++)
-            acc[n] = C{R(0), R(0)};
+            for (int n = 0; n < K; n++)
+                acc[n] = 0ull;
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            const C a = E[g | Spread<MASK>(k)];
+            for (int k = 0; k < K; k++) {
+                const C a = E[g | Spread<MASK>(k)];
 #pragma unroll
-            for (int n0 = 0; n0 < K; n0 += 2) {
-                // two matrix entries per shared-memory load (rows are 32-byte aligned: np % 4 == 0)
-                C r[2];
-                if constexpr (sizeof(C) == 8) {
-                    const float4 v = *reinterpret_cast<const float4 *>(B + k * np + n0);
-                    r[0] = C{v.x, v.y};
-                    r[1] = C{v.z, v.w};
-                }
-                else {
-                    r[0] = B[k * np + n0];
-                    r[1] = B[k * np + n0 + 1];
-                }
-                CMulAdd(acc[n0], a, r[0]);
-                CMulAdd(acc[n0 + 1], a, r[1]);
+                for (int n = 0; n < K; n++)
+                    CMulAdd2(acc[n], a, B[k * NP + n]);
             }
-        }
 #pragma unroll
-        for (int n = 0; n < K; n++)
-            E[g | Spread<MASK>(n)] = acc[n];
+            for (int n = 0; n < K; n++)
+                E[g | Spread<MASK>(n)] = Unpack2(acc[n]);
+        }
+        else {
+            C acc[K];
+#pragma unroll
+            for (int n = 0; n < K; n++)
+                acc[n] = C{R(0), R(0)};
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const C a = E[g | Spread<MASK>(k)];
+#pragma unroll
+                for (int n = 0; n < K; n++)
+                    CMulAdd(acc[n], a, B[k * NP + n]);
+            }
+#pragma unroll
+            for (int n = 0; n < K; n++)
+                E[g | Spread<MASK>(n)] = acc[n];
+        }
     }
 }
 
 template <typename R, int NL>
 __device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1 << NL],
-                                                   const typename Cplx<R>::type *__restrict__ B,
-                                                   const int np, const int mask)
+                                                   const typename StageB<R>::type *__restrict__ B,
+                                                   const int mask)
 {
     if constexpr (NL == 4) {
         switch (mask) {
-        case 1: ApplyLocal<R, NL, 1>(E, B, np); break;
-        case 2: ApplyLocal<R, NL, 2>(E, B, np); break;
-        case 3: ApplyLocal<R, NL, 3>(E, B, np); break;
-        case 4: ApplyLocal<R, NL, 4>(E, B, np); break;
-        case 5: ApplyLocal<R, NL, 5>(E, B, np); break;
-        case 6: ApplyLocal<R, NL, 6>(E, B, np); break;
-        case 7: ApplyLocal<R, NL, 7>(E, B, np); break;
-        case 8: ApplyLocal<R, NL, 8>(E, B, np); break;
-        case 9: ApplyLocal<R, NL, 9>(E, B, np); break;
-        case 10: ApplyLocal<R, NL, 10>(E, B, np); break;
-        case 11: ApplyLocal<R, NL, 11>(E, B, np); break;
-        case 12: ApplyLocal<R, NL, 12>(E, B, np); break;
-        case 13: ApplyLocal<R, NL, 13>(E, B, np); break;
-        case 14: ApplyLocal<R, NL, 14>(E, B, np); break;
-        default: ApplyLocal<R, NL, 15>(E, B, np); break;
+        case 1: ApplyLocal<R, NL, 1>(E, B); break;
+        case 2: ApplyLocal<R, NL, 2>(E, B); break;
+        case 3: ApplyLocal<R, NL, 3>(E, B); break;
+        case 4: ApplyLocal<R, NL, 4>(E, B); break;
+        case 5: ApplyLocal<R, NL, 5>(E, B); break;
+        case 6: ApplyLocal<R, NL, 6>(E, B); break;
+        case 7: ApplyLocal<R, NL, 7>(E, B); break;
+        case 8: ApplyLocal<R, NL, 8>(E, B); break;
+        case 9: ApplyLocal<R, NL, 9>(E, B); break;
+        case 10: ApplyLocal<R, NL, 10>(E, B); break;
+        case 11: ApplyLocal<R, NL, 11>(E, B); break;
+        case 12: ApplyLocal<R, NL, 12>(E, B); break;
+        case 13: ApplyLocal<R, NL, 13>(E, B); break;
+        case 14: ApplyLocal<R, NL, 14>(E, B); break;
+        default: ApplyLocal<R, NL, 15>(E, B); break;
         }
     }
     else {
         switch (mask) {
-        case 1: ApplyLocal<R, NL, 1>(E, B, np); break;
-        case 2: ApplyLocal<R, NL, 2>(E, B, np); break;
-        case 3: ApplyLocal<R, NL, 3>(E, B, np); break;
-        case 4: ApplyLocal<R, NL, 4>(E, B, np); break;
-        case 5: ApplyLocal<R, NL, 5>(E, B, np); break;
-        case 6: ApplyLocal<R, NL, 6>(E, B, np); break;
-        default: ApplyLocal<R, NL, 7>(E, B, np); break;
+        case 1: ApplyLocal<R, NL, 1>(E, B); break;
+        case 2: ApplyLocal<R, NL, 2>(E, B); break;
+        case 3: ApplyLocal<R, NL, 3>(E, B); break;
+        case 4: ApplyLocal<R, NL, 4>(E, B); break;
+        case 5: ApplyLocal<R, NL, 5>(E, B); break;
+        case 6: ApplyLocal<R, NL, 6>(E, B); break;
+        default: ApplyLocal<R, NL, 7>(E, B); break;
         }
     }
 }
 
 template <typename R>
 __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__restrict__ tile,
-                                                   const typename Cplx<R>::type *__restrict__ Bm,
+                                                   const typename StageB<R>::type *__restrict__ Bs,
                                                    const ChainParams &p, const ChainStageParams &g,
                                                    const uint16_t *__restrict__ gtab, const int tid)
 {
@@ -290,12 +330,22 @@ __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__res
             E[e] = tile[base ^ l01[e & 3] ^ l23[e >> 2]];
         for (int t = 0; t < g.count; t++) {
             const ChainStepParams &q = p.step[g.first + t];
-            ApplyLocalDispatch<R, NL>(E, Bm + q.b_off, q.np, g.mask[t]);
+            ApplyLocalDispatch<R, NL>(E, Bs + q.b_off, g.mask[t]);
         }
 #pragma unroll
         for (int e = 0; e < NE; e++)
             tile[base ^ l01[e & 3] ^ l23[e >> 2]] = E[e];
     }
+}
+
+template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems)
+{
+    using C = typename Cplx<R>::type;
+    size_t b = sizeof(C) * (size_t(1) << log_tile);
+    b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
+    if (sizeof(R) == 4)
+        b += sizeof(float4) * static_cast<size_t>(resident_elems);
+    return b;
 }
 
 template <typename R, int MINB>
@@ -308,6 +358,10 @@ __global__ void __launch_bounds__(kChainThreads, MINB)
     extern __shared__ __align__(16) unsigned char chain_smem[];
     C *tile = reinterpret_cast<C *>(chain_smem);
     C *Bm = tile + (1 << p.log_tile);
+    // complex64: a second copy of the matrices in the packed-FMA form used by the register stages
+    typename StageB<R>::type *Bs = reinterpret_cast<typename StageB<R>::type *>(Bm);
+    if constexpr (sizeof(R) == 4)
+        Bs = reinterpret_cast<float4 *>(Bm + ((p.resident_elems + 1) & ~1));
     const int tid = threadIdx.x;
 
     // resident operands -> shared memory as K x np matrices (columns n >= N are zero)
@@ -323,6 +377,8 @@ __global__ void __launch_bounds__(kChainThreads, MINB)
             if (static_cast<int>(n) < N)
                 v = __ldg(Rs + (Deposit(k, q.rk, q.log_k) | Deposit(n, q.rn, q.log_n)));
             Bm[q.b_off + e] = v;
+            if constexpr (sizeof(R) == 4)
+                Bs[q.b_off + e] = make_float4(v.x, v.y, -v.y, v.x);
         }
     }
 
@@ -367,7 +423,7 @@ __global__ void __launch_bounds__(kChainThreads, MINB)
         for (int sg = 0; sg < p.n_stages; sg++) {
             const ChainStageParams &g = p.stage[sg];
             if (g.kind == 1) {
-                ChainRegisterStage<R>(tile, Bm, p, g, p.stage_tab[sg], tid);
+                ChainRegisterStage<R>(tile, Bs, p, g, p.stage_tab[sg], tid);
             }
             else {
                 const ChainStepParams &q = p.step[g.first];
@@ -417,7 +473,7 @@ int LaunchChainT(const ChainParams &p, const ChainPtrs &ptrs, const void *x0, vo
                  cudaStream_t stream)
 {
     using C = typename Cplx<R>::type;
-    const size_t smem = sizeof(C) * ((size_t(1) << p.log_tile) + static_cast<size_t>(p.resident_elems));
+    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems);
     auto kernel = ChainKernel<R, MINB>;
     if (smem > 48 * 1024)
         JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -565,6 +621,15 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     if (!PlanChain(spec, max_tile_bits, wide, &lay, why) &&
         !PlanChain(spec, max_tile_bits, wide - 1, &lay, why))
         return 1;
+    {
+        const size_t smem = spec.elem_bytes == 8
+                                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems)
+                                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems);
+        if (smem > 100 * 1024) { // two CTAs per SM
+            *why = "shared memory";
+            return 1;
+        }
+    }
     // the bit-level replay must agree with the index-level one
     {
         std::vector<int> chk;
@@ -599,13 +664,8 @@ int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *x
     std::memset(&ptrs, 0, sizeof(ptrs));
     for (int s = 0; s < op.n_steps; s++)
         ptrs.r[s] = r[s];
-    static const int minb = [] {
-        const char *e = getenv("JB_CHAIN_MINB");
-        return e ? atoi(e) : 2;
-    }();
     if (op.dtype == JB_C64)
-        return minb == 3 ? LaunchChainT<float, 3>(p, ptrs, x0, xk, stream)
-                         : LaunchChainT<float, 2>(p, ptrs, x0, xk, stream);
+        return LaunchChainT<float, 2>(p, ptrs, x0, xk, stream);
     return LaunchChainT<double, 2>(p, ptrs, x0, xk, stream);
 }
 

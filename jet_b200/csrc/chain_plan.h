@@ -77,8 +77,8 @@ struct ChainParams {
     uint8_t outer_out[kChainMaxOuterBits]; // X_k address bit of tile-number bit q
     ChainStepParams step[kChainMaxSteps];
     ChainStageParams stage[kChainMaxSteps];
-    // thread-independent parts of the index maps, tabulated for 256-thread CTAs: entry j is the
-    // contribution of work-index bits 8.. (j = index >> 8)
+    // thread-independent parts of the index maps, tabulated for the CTA size: entry j is the
+    // contribution of the work-index bits above the thread id (j = index >> kChainLogThreads)
     unsigned long long in_gtab[kChainTabLen], out_gtab[kChainTabLen];
     uint16_t in_stab[kChainTabLen], out_stab[kChainTabLen];
     uint16_t stage_tab[kChainMaxSteps][kChainTabLen];

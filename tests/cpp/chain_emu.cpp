@@ -18,8 +18,8 @@ using namespace jb;
 using cd = std::complex<double>;
 
 namespace {
-constexpr int kThreads = 256;
-constexpr int kLogThreads = 8;
+constexpr int kLogThreads = kChainLogThreads;
+constexpr int kThreads = 1 << kLogThreads;
 
 // worst number of distinct addresses that fall into one bank group within a half/quarter warp
 int ConflictDegree(const std::vector<unsigned> &addr_by_lane, int elem_bytes)
