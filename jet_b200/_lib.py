@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libjetb200.so")
+LIB_PATH = os.environ.get("JETB200_LIB") or os.path.join(HERE, "lib", "libjetb200.so")
 
 JB_C64, JB_C128 = 0, 1
 JB_MAX_RANK = 64

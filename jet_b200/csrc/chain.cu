@@ -96,7 +96,8 @@ template <typename R, int KC, int G>
 __device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ tile,
                                           const typename Cplx<R>::type *__restrict__ Bm,
                                           const ChainStepParams &q,
-                                          const uint16_t *__restrict__ gtab, const int tid)
+                                          const uint16_t *__restrict__ gtab, const unsigned a_tid,
+                                          const int tid)
 {
     using C = typename Cplx<R>::type;
     const int log_g = q.log_g;
@@ -121,8 +122,6 @@ __device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ t
     const unsigned ncol2 = log_n >= 3 ? q.ncol[2] : 0u;
     const unsigned ncol3 = log_n >= 4 ? q.ncol[3] : 0u;
 
-    const int tid_bits = log_g < kLogChainThreads ? log_g : kLogChainThreads;
-    const unsigned a_tid = Lin(static_cast<unsigned>(tid), q.gcol, tid_bits);
     const bool t_ok = tid < (1 << log_g);
     const int per_thread = log_g > kLogChainThreads ? (1 << (log_g - kLogChainThreads)) : 1;
     const C *bbase = Bm + q.b_off;
@@ -221,28 +220,53 @@ __device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
     constexpr int K = 1 << LK;
     constexpr int NE = 1 << NL;
     constexpr int NP = K < 4 ? 4 : K; // row stride of the matrix: ChainStepParams::np for K == N
-    // group by group, in place: the K inputs of a group are replaced by its K outputs
+    if constexpr (sizeof(R) == 4) {
+        // All groups at once: out[] accumulates every output while the matrix streams through a
+        // small register ring, one chunk of CH entries (one k, CH consecutive n) per step of the
+        // software pipeline; chunk c + D is loaded before chunk c is consumed, so the shared-memory
+        // latency of the matrix loads hides behind 32+ packed FMAs instead of stalling each of them.
+        constexpr int CH = K < 4 ? K : 4;
+        constexpr int CPR = K / CH;       // chunks per matrix row
+        constexpr int NCH = K * CPR;      // chunks per step
+        constexpr int D = K <= 4 ? 1 : 2; // prefetch distance
+        unsigned long long out[NE];
 #pragma unroll
-    for (int g = 0; g < NE; g++) {
-        if (g & MASK)
-            continue;
-        if constexpr (sizeof(R) == 4) {
-            unsigned long long acc[K];
+        for (int e = 0; e < NE; e++)
+            out[e] = 0ull;
+        float4 ring[D + 1][CH];
 #pragma unroll
-            for (int n = 0; n < K; n++)
-                acc[n] = 0ull;
+        for (int c = 0; c < D && c < NCH; c++)
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const C a = E[g | Spread<MASK>(k)];
+            for (int nn = 0; nn < CH; nn++)
+                ring[c][nn] = B[(c / CPR) * NP + (c % CPR) * CH + nn];
 #pragma unroll
-                for (int n = 0; n < K; n++)
-                    CMulAdd2(acc[n], a, B[k * NP + n]);
+        for (int c = 0; c < NCH; c++) {
+            if (c + D < NCH) {
+#pragma unroll
+                for (int nn = 0; nn < CH; nn++)
+                    ring[(c + D) % (D + 1)][nn] = B[((c + D) / CPR) * NP + ((c + D) % CPR) * CH + nn];
             }
+            const int k = c / CPR, n0 = (c % CPR) * CH;
 #pragma unroll
-            for (int n = 0; n < K; n++)
-                E[g | Spread<MASK>(n)] = Unpack2(acc[n]);
+            for (int nn = 0; nn < CH; nn++) {
+#pragma unroll
+                for (int g = 0; g < NE; g++) {
+                    if (g & MASK)
+                        continue;
+                    CMulAdd2(out[g | Spread<MASK>(n0 + nn)], E[g | Spread<MASK>(k)], ring[c % (D + 1)][nn]);
+                }
+            }
         }
-        else {
+#pragma unroll
+        for (int e = 0; e < NE; e++)
+            E[e] = Unpack2(out[e]);
+    }
+    else {
+        // group by group, in place: the K inputs of a group are replaced by its K outputs
+#pragma unroll
+        for (int g = 0; g < NE; g++) {
+            if (g & MASK)
+                continue;
             C acc[K];
 #pragma unroll
             for (int n = 0; n < K; n++)
@@ -281,8 +305,7 @@ __device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1
         case 11: ApplyLocal<R, NL, 11>(E, B); break;
         case 12: ApplyLocal<R, NL, 12>(E, B); break;
         case 13: ApplyLocal<R, NL, 13>(E, B); break;
-        case 14: ApplyLocal<R, NL, 14>(E, B); break;
-        default: ApplyLocal<R, NL, 15>(E, B); break;
+        default: ApplyLocal<R, NL, 14>(E, B); break; // K = 16 steps never enter a register stage
         }
     }
     else {
@@ -301,18 +324,18 @@ __device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1
 template <typename R>
 __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__restrict__ tile,
                                                    const typename StageB<R>::type *__restrict__ Bs,
-                                                   const ChainParams &p, const ChainStageParams &g,
-                                                   const uint16_t *__restrict__ gtab, const int tid)
+                                                   const ChainStageParams &g,
+                                                   const uint16_t *__restrict__ gtab,
+                                                   const unsigned a_tid, const int tid)
 {
     using C = typename Cplx<R>::type;
     constexpr int NL = sizeof(R) == 4 ? 4 : 3;
     constexpr int NE = 1 << NL;
     const int log_g = g.log_g;
-    const int tid_bits = log_g < kLogChainThreads ? log_g : kLogChainThreads;
     if (tid >= (1 << log_g))
         return;
-    const unsigned a_tid = Lin(static_cast<unsigned>(tid), g.gcol, tid_bits);
     const int per_thread = log_g > kLogChainThreads ? (1 << (log_g - kLogChainThreads)) : 1;
+    const int count = g.count;
     unsigned l01[4], l23[4];
     l01[0] = 0;
     l01[1] = g.lcol[0];
@@ -328,9 +351,12 @@ __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__res
 #pragma unroll
         for (int e = 0; e < NE; e++)
             E[e] = tile[base ^ l01[e & 3] ^ l23[e >> 2]];
-        for (int t = 0; t < g.count; t++) {
-            const ChainStepParams &q = p.step[g.first + t];
-            ApplyLocalDispatch<R, NL>(E, Bs + q.b_off, g.mask[t]);
+        // the descriptor of step t + 1 is fetched while step t computes
+        unsigned desc = g.desc[0];
+        for (int t = 0; t < count; t++) {
+            const unsigned cur = desc;
+            desc = g.desc[(t + 1) & (kChainMaxStageSteps - 1)];
+            ApplyLocalDispatch<R, NL>(E, Bs + (cur >> 8), static_cast<int>(cur & 0xffu));
         }
 #pragma unroll
         for (int e = 0; e < NE; e++)
@@ -338,31 +364,76 @@ __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__res
     }
 }
 
+// ---- the kernel -----------------------------------------------------------------------------------
+// One persistent 512-thread CTA per SM, warp-specialised over a ring of three tile buffers:
+//   warps 0-7   compute: apply the chain to tile i in place, stage by stage (FMA pipe only — these
+//               warps never touch global memory);
+//   warps 8-11  load:    cp.async tile i+1 / i+2 from X_0 into a free buffer;
+//   warps 12-15 store:   write tile i-1 from its buffer to X_k.
+// The memory warps absorb the LSU back-pressure of the 64 KB tile transfers, so the HBM traffic of two
+// tiles is in flight while the FMA pipe works on a third.  Hand-off is by named barriers
+// (bar.arrive by the producer, bar.sync by the consumer): full[b] load -> compute, done[b] compute ->
+// store, free[b] store -> load.
+constexpr int kChainBuffers = 3;
+constexpr int kChainLoadThreads = 128;
+constexpr int kChainStoreThreads = 128;
+constexpr int kChainCtaThreads = kChainThreads + kChainLoadThreads + kChainStoreThreads;
+constexpr int kBarCompute = 1, kBarFull = 2, kBarDone = 5, kBarFree = 8;
+
+__device__ __forceinline__ void BarSync(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void BarArrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems)
 {
     using C = typename Cplx<R>::type;
-    size_t b = sizeof(C) * (size_t(1) << log_tile);
+    size_t b = sizeof(C) * kChainBuffers * (size_t(1) << log_tile);
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
     if (sizeof(R) == 4)
         b += sizeof(float4) * static_cast<size_t>(resident_elems);
+    b += sizeof(uint16_t) * kChainMaxSteps * kChainThreads; // per-thread stage offsets
     return b;
 }
 
-template <typename R, int MINB>
-__global__ void __launch_bounds__(kChainThreads, MINB)
+template <typename R>
+__global__ void __launch_bounds__(kChainCtaThreads, 1)
     ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
                 typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
                 const __grid_constant__ ChainPtrs rp)
 {
     using C = typename Cplx<R>::type;
     extern __shared__ __align__(16) unsigned char chain_smem[];
-    C *tile = reinterpret_cast<C *>(chain_smem);
-    C *Bm = tile + (1 << p.log_tile);
+    C *tiles = reinterpret_cast<C *>(chain_smem);
+    const int tile_elems = 1 << p.log_tile;
+    C *Bm = tiles + kChainBuffers * tile_elems;
     // complex64: a second copy of the matrices in the packed-FMA form used by the register stages
     typename StageB<R>::type *Bs = reinterpret_cast<typename StageB<R>::type *>(Bm);
-    if constexpr (sizeof(R) == 4)
+    uint16_t *atid;
+    if constexpr (sizeof(R) == 4) {
         Bs = reinterpret_cast<float4 *>(Bm + ((p.resident_elems + 1) & ~1));
+        atid = reinterpret_cast<uint16_t *>(Bs + p.resident_elems);
+    }
+    else {
+        atid = reinterpret_cast<uint16_t *>(Bm + ((p.resident_elems + 1) & ~1));
+    }
     const int tid = threadIdx.x;
+
+    // per-thread part of every stage's tile address (tile independent): one table lookup per stage
+    // instead of a bit loop over kernel parameters in the hot path
+    if (tid < kChainThreads) {
+        for (int sg = 0; sg < p.n_stages; sg++) {
+            const ChainStageParams &g = p.stage[sg];
+            const uint16_t *gc = g.kind == 1 ? g.gcol : p.step[g.first].gcol;
+            const int lg = g.kind == 1 ? g.log_g : p.step[g.first].log_g;
+            atid[sg * kChainThreads + tid] =
+                static_cast<uint16_t>(Lin(tid, gc, lg < kLogChainThreads ? lg : kLogChainThreads));
+        }
+    }
 
     // resident operands -> shared memory as K x np matrices (columns n >= N are zero)
     for (int s = 0; s < p.n_steps; s++) {
@@ -371,7 +442,7 @@ __global__ void __launch_bounds__(kChainThreads, MINB)
         const int np = q.np;
         const int N = 1 << q.log_n;
         const int total = np << q.log_k;
-        for (int e = tid; e < total; e += kChainThreads) {
+        for (int e = tid; e < total; e += kChainCtaThreads) {
             const unsigned k = e / np, n = e % np;
             C v = C{R(0), R(0)};
             if (static_cast<int>(n) < N)
@@ -381,108 +452,156 @@ __global__ void __launch_bounds__(kChainThreads, MINB)
                 Bs[q.b_off + e] = make_float4(v.x, v.y, -v.y, v.x);
         }
     }
-
-    const int in_tid_bits = min(p.log_tile_in, kLogChainThreads);
-    const int out_tid_bits = min(p.log_tile_out, kLogChainThreads);
-
-    // per-thread parts of the load / store index maps (tile independent)
-    const unsigned in_s_tid = Lin(tid, p.in_scol, in_tid_bits);
-    const unsigned out_s_tid = Lin(tid, p.out_scol, out_tid_bits);
-    const unsigned long long in_g_tid = Deposit(tid, p.in_gbit, in_tid_bits);
-    const unsigned long long out_g_tid = Deposit(tid, p.out_gbit, out_tid_bits);
-    const bool in_ok = tid < (1 << p.log_tile_in);
-    const bool out_ok = tid < (1 << p.log_tile_out);
-    const int in_iters = p.log_tile_in > kLogChainThreads ? 1 << (p.log_tile_in - kLogChainThreads) : 1;
-    const int out_iters = p.log_tile_out > kLogChainThreads ? 1 << (p.log_tile_out - kLogChainThreads) : 1;
     __syncthreads();
 
-    constexpr int U = 8;
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const unsigned long long in_base = Deposit(static_cast<unsigned long long>(t), p.outer_in, p.log_outer);
-        const unsigned long long out_base = Deposit(static_cast<unsigned long long>(t), p.outer_out, p.log_outer);
+    const long long n_my = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x; // tiles of this CTA
+    constexpr int kFullCount = kChainLoadThreads + kChainThreads;
+    constexpr int kDoneCount = kChainThreads + kChainStoreThreads;
+    constexpr int kFreeCount = kChainStoreThreads + kChainLoadThreads;
 
-        // ---- load: X_0 tile -> shared memory (coalesced along the low X_0 address bits) ----------
-        // cp.async: every element of the tile is in flight at once and no register is staged
-        if (in_ok) {
-            const C *src = X0 + (in_base | in_g_tid);
-            const unsigned tile_s = static_cast<unsigned>(__cvta_generic_to_shared(tile));
-#pragma unroll 8
-            for (int j = 0; j < in_iters; j++) {
-                const unsigned dst = tile_s + (in_s_tid ^ p.in_stab[j]) * static_cast<unsigned>(sizeof(C));
-                const C *g = src + p.in_gtab[j];
-                if constexpr (sizeof(C) == 8)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
-                else
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+    if (tid < kChainThreads) {
+        // ================================ compute warps =========================================
+        for (long long i = 0; i < n_my; i++) {
+            const int b = static_cast<int>(i % kChainBuffers);
+            C *tile = tiles + b * tile_elems;
+            BarSync(kBarFull + b, kFullCount);
+            for (int sg = 0; sg < p.n_stages; sg++) {
+                const ChainStageParams &g = p.stage[sg];
+                const unsigned a_tid = atid[sg * kChainThreads + tid];
+                if (g.kind == 1) {
+                    ChainRegisterStage<R>(tile, Bs, g, p.stage_tab[sg], a_tid, tid);
+                }
+                else {
+                    const ChainStepParams &q = p.step[g.first];
+                    constexpr bool kF = sizeof(R) == 4;
+                    switch (q.log_k) {
+                    case 0:
+                        ChainStep<R, 1, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        break;
+                    case 1:
+                        ChainStep<R, 2, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        break;
+                    case 2:
+                        ChainStep<R, 4, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        break;
+                    case 3:
+                        ChainStep<R, 8, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        break;
+                    default:
+                        ChainStep<R, 16, 1>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        break;
+                    }
+                }
+                if (sg + 1 < p.n_stages)
+                    BarSync(kBarCompute, kChainThreads);
             }
+            BarArrive(kBarDone + b, kDoneCount);
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
-
-        // ---- the chain, in place ---------------------------------------------------------------
-        for (int sg = 0; sg < p.n_stages; sg++) {
-            const ChainStageParams &g = p.stage[sg];
-            if (g.kind == 1) {
-                ChainRegisterStage<R>(tile, Bs, p, g, p.stage_tab[sg], tid);
-            }
-            else {
-                const ChainStepParams &q = p.step[g.first];
-                constexpr bool kF = sizeof(R) == 4;
-                switch (q.log_k) {
-                case 0:
-                    ChainStep<R, 1, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], tid);
-                    break;
-                case 1:
-                    ChainStep<R, 2, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], tid);
-                    break;
-                case 2:
-                    ChainStep<R, 4, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], tid);
-                    break;
-                case 3:
-                    ChainStep<R, 8, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], tid);
-                    break;
-                default:
-                    ChainStep<R, 16, 1>(tile, Bm, q, p.stage_tab[sg], tid);
-                    break;
+    }
+    else if (tid < kChainThreads + kChainLoadThreads) {
+        // ================================== load warps ===========================================
+        // X_0 tile -> shared memory, coalesced along the low X_0 address bits.  Each thread plays two
+        // of the 256 load lanes the index tables are built for.
+        const int lt = tid - kChainThreads;
+        const int tid_bits = min(p.log_tile_in, kLogChainThreads);
+        const int iters = p.log_tile_in > kLogChainThreads ? 1 << (p.log_tile_in - kLogChainThreads) : 1;
+        unsigned s_lane[2];
+        unsigned long long g_lane[2];
+        bool ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int v = lt + h * kChainLoadThreads;
+            s_lane[h] = Lin(v, p.in_scol, tid_bits);
+            g_lane[h] = Deposit(v, p.in_gbit, tid_bits);
+            ok[h] = v < (1 << p.log_tile_in);
+        }
+        const unsigned tiles_s = static_cast<unsigned>(__cvta_generic_to_shared(tiles));
+        for (long long i = 0; i < n_my; i++) {
+            const int b = static_cast<int>(i % kChainBuffers);
+            const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(i) * gridDim.x;
+            const unsigned long long base = Deposit(t, p.outer_in, p.log_outer);
+            if (i >= kChainBuffers)
+                BarSync(kBarFree + b, kFreeCount);
+            const unsigned buf_s = tiles_s + static_cast<unsigned>(b * tile_elems * sizeof(C));
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (!ok[h])
+                    continue;
+                const C *src = X0 + (base | g_lane[h]);
+#pragma unroll 4
+                for (int j = 0; j < iters; j++) {
+                    const unsigned dst = buf_s + (s_lane[h] ^ p.in_stab[j]) * static_cast<unsigned>(sizeof(C));
+                    const C *g = src + p.in_gtab[j];
+                    if constexpr (sizeof(C) == 8)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
+                    else
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
                 }
             }
-            __syncthreads();
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __threadfence_block();
+            BarArrive(kBarFull + b, kFullCount);
         }
-
-        // ---- store: shared memory -> X_k tile (coalesced along the low X_k address bits) ------------
-        if (out_ok) {
-            C *dst = Xk + (out_base | out_g_tid);
-            for (int j0 = 0; j0 < out_iters; j0 += U) {
-                C v[U];
+    }
+    else {
+        // ================================== store warps ==========================================
+        // shared memory -> X_k tile, coalesced along the low X_k address bits
+        const int lt = tid - kChainThreads - kChainLoadThreads;
+        const int tid_bits = min(p.log_tile_out, kLogChainThreads);
+        const int iters = p.log_tile_out > kLogChainThreads ? 1 << (p.log_tile_out - kLogChainThreads) : 1;
+        unsigned s_lane[2];
+        unsigned long long g_lane[2];
+        bool ok[2];
 #pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (j0 + u < out_iters)
-                        v[u] = tile[out_s_tid ^ p.out_stab[j0 + u]];
+        for (int h = 0; h < 2; h++) {
+            const int v = lt + h * kChainStoreThreads;
+            s_lane[h] = Lin(v, p.out_scol, tid_bits);
+            g_lane[h] = Deposit(v, p.out_gbit, tid_bits);
+            ok[h] = v < (1 << p.log_tile_out);
+        }
+        for (long long i = 0; i < n_my; i++) {
+            const int b = static_cast<int>(i % kChainBuffers);
+            const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(i) * gridDim.x;
+            const unsigned long long base = Deposit(t, p.outer_out, p.log_outer);
+            const C *buf = tiles + b * tile_elems;
+            BarSync(kBarDone + b, kDoneCount);
 #pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (j0 + u < out_iters)
-                        dst[p.out_gtab[j0 + u]] = v[u];
+            for (int h = 0; h < 2; h++) {
+                if (!ok[h])
+                    continue;
+                C *dst = Xk + (base | g_lane[h]);
+                constexpr int U = 8;
+                for (int j0 = 0; j0 < iters; j0 += U) {
+                    C v[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (j0 + u < iters)
+                            v[u] = buf[s_lane[h] ^ p.out_stab[j0 + u]];
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (j0 + u < iters)
+                            dst[p.out_gtab[j0 + u]] = v[u];
+                }
             }
+            if (i + kChainBuffers < n_my)
+                BarArrive(kBarFree + b, kFreeCount);
         }
-        __syncthreads();
     }
 }
 
-template <typename R, int MINB>
+template <typename R>
 int LaunchChainT(const ChainParams &p, const ChainPtrs &ptrs, const void *x0, void *xk,
                  cudaStream_t stream)
 {
     using C = typename Cplx<R>::type;
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems);
-    auto kernel = ChainKernel<R, MINB>;
+    auto kernel = ChainKernel<R>;
     if (smem > 48 * 1024)
         JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-    const long long resident =
-        static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kChainThreads, smem);
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(p.n_tiles, resident)));
-    kernel<<<grid, kChainThreads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p,
-                                                  ptrs);
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(p.n_tiles, NumSMs())));
+    kernel<<<grid, kChainCtaThreads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p,
+                                                     ptrs);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -625,7 +744,7 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
         const size_t smem = spec.elem_bytes == 8
                                 ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems)
                                 : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems);
-        if (smem > 100 * 1024) { // two CTAs per SM
+        if (smem > 227 * 1024) {
             *why = "shared memory";
             return 1;
         }
@@ -665,8 +784,8 @@ int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *x
     for (int s = 0; s < op.n_steps; s++)
         ptrs.r[s] = r[s];
     if (op.dtype == JB_C64)
-        return LaunchChainT<float, 2>(p, ptrs, x0, xk, stream);
-    return LaunchChainT<double, 2>(p, ptrs, x0, xk, stream);
+        return LaunchChainT<float>(p, ptrs, x0, xk, stream);
+    return LaunchChainT<double>(p, ptrs, x0, xk, stream);
 }
 
 } // namespace jb

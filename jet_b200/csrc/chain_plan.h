@@ -57,7 +57,7 @@ struct ChainStageParams {
     uint8_t kind, first, count, log_g;
     uint16_t gcol[kChainMaxTileBits];      // tile address column of register-tile index bit q
     uint16_t lcol[kChainLocalBits];        // tile address column of local bit q
-    uint8_t mask[kChainMaxStageSteps];     // local bits contracted (and re-created) by each step
+    uint32_t desc[kChainMaxStageSteps];    // per step: local-bit mask | matrix offset (b_off) << 8
 };
 
 struct ChainParams {
@@ -408,13 +408,13 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
             std::vector<int> occupied = sp[i].alive_after; // invariant over a run of in-place steps
             std::sort(occupied.begin(), occupied.end());
             if (!sp[i].in_place || static_cast<int>(occupied.size()) < local_bits ||
-                static_cast<int>(sp[i].k.size()) > local_bits) {
+                static_cast<int>(sp[i].k.size()) > 3) {
                 i++;
                 continue;
             }
             std::set<int> local(sp[i].k.begin(), sp[i].k.end());
             int j = i + 1;
-            while (j < n_steps && sp[j].in_place && j - i < kChainMaxStageSteps) {
+            while (j < n_steps && sp[j].in_place && sp[j].k.size() <= 3 && j - i < kChainMaxStageSteps) {
                 std::set<int> u = local;
                 u.insert(sp[j].k.begin(), sp[j].k.end());
                 if (static_cast<int>(u.size()) > local_bits)
@@ -439,7 +439,7 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
                 unsigned m = 0;
                 for (int pp : sp[t].k)
                     m |= 1u << (std::find(lvec.begin(), lvec.end(), pp) - lvec.begin());
-                G.mask[t - i] = static_cast<uint8_t>(m);
+                G.desc[t - i] = m | (static_cast<uint32_t>(P.step[t].b_off) << 8);
             }
             i = j;
         }

@@ -147,7 +147,9 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                             }
                             for (int t = 0; t < G.count; t++) {
                                 const ChainStepParams &q = p.step[G.first + t];
-                                const int mask = G.mask[t];
+                                const int mask = G.desc[t] & 0xff;
+                                if ((G.desc[t] >> 8) != q.b_off)
+                                    hazards += 1000;
                                 std::vector<int> mpos;
                                 for (int b = 0; b < NL; b++)
                                     if (mask & (1 << b))
