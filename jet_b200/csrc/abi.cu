@@ -308,13 +308,44 @@ int jb_chain_info(const jb_chain_desc_t *desc, jb_chain_info_t *info)
     return 0;
 }
 
+namespace {
+// Operator-level chains share one constant-bank slot per device: calls are serialised with a mutex
+// and, across streams, with an event recorded after each launch.
+struct OperatorChainState {
+    void *staging = nullptr;
+    cudaEvent_t done = nullptr;
+};
+std::mutex g_op_chain_mutex;
+OperatorChainState g_op_chain[64];
+
+int LaunchOperatorChain(const ChainOp &op, const void *d_x, const void *const *d_r, void *d_out,
+                        cudaStream_t stream)
+{
+    int dev = 0;
+    JB_CUDA(cudaGetDevice(&dev));
+    JB_REQUIRE(dev >= 0 && dev < 64, "chain: device index out of range");
+    std::lock_guard<std::mutex> lock(g_op_chain_mutex);
+    OperatorChainState &st = g_op_chain[dev];
+    if (st.staging == nullptr) {
+        JB_CUDA(cudaMalloc(&st.staging, ChainStagingBytes()));
+        JB_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    }
+    else {
+        JB_CUDA(cudaStreamWaitEvent(stream, st.done, 0)); // the previous call may be on another stream
+    }
+    JB_TRY(LaunchChain(op, d_x, d_r, d_out, st.staging, ChainOperatorSlot(), stream));
+    JB_CUDA(cudaEventRecord(st.done, stream));
+    return 0;
+}
+} // namespace
+
 int jb_contract_chain(const jb_chain_desc_t *desc, const void *d_x, const void *const *d_r,
                       void *d_out, void *stream)
 {
     JB_REQUIRE(d_x && d_r && d_out, "chain: null buffer");
     ChainOp op;
     JB_TRY(BuildChain(desc, &op));
-    return LaunchChain(op, d_x, d_r, d_out, static_cast<cudaStream_t>(stream));
+    return LaunchOperatorChain(op, d_x, d_r, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int jb_contract_chain_host(const jb_chain_desc_t *desc, const void *h_x, const void *const *h_r,
@@ -350,7 +381,7 @@ int jb_contract_chain_host(const jb_chain_desc_t *desc, const void *h_x, const v
         JB_CUDA(cudaMemcpy(static_cast<unsigned char *>(rs.p) + roff[s], h_r[s], b, cudaMemcpyHostToDevice));
         rp[s] = static_cast<unsigned char *>(rs.p) + roff[s];
     }
-    JB_TRY(LaunchChain(op, x.p, rp.data(), out.p, nullptr));
+    JB_TRY(LaunchOperatorChain(op, x.p, rp.data(), out.p, nullptr));
     JB_CUDA(cudaMemcpy(h_out, out.p, bout, cudaMemcpyDeviceToHost));
     return 0;
 }

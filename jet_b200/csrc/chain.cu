@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "chain_plan.h"
 #include "common.cuh"
@@ -210,10 +211,32 @@ template <> struct StageB<double> {
     using type = double2;
 };
 
+// The matrices of the register-stage steps live in the CONSTANT bank: every thread of a warp reads
+// the same entry, so the loads go through the uniform datapath (LDCU into a uniform register that the
+// packed FMA takes directly as an operand) and never touch the LSU, the shared-memory pipe or the
+// per-lane register file.  Measured (tools/micro/ffma2_mix.cu): 97 % of the FMA pipe with two warps
+// per scheduler, against 53 % when the same entries come from shared memory.
+// One 16 KB region per slot; a plan (or the operator-level entry point) owns a slot while it lives.
+constexpr int kChainConstSlots = 3;
+constexpr int kChainConstEntries = 1024; // 16-byte entries per slot
+__constant__ uint4 g_chain_const[kChainConstSlots * kChainConstEntries];
+
+template <typename R> __device__ __forceinline__ typename StageB<R>::type ConstB(int idx);
+template <> __device__ __forceinline__ float4 ConstB<float>(int idx)
+{
+    const uint4 v = g_chain_const[idx];
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+template <> __device__ __forceinline__ double2 ConstB<double>(int idx)
+{
+    const uint4 v = g_chain_const[idx];
+    return make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
+}
+
 // NL local bits: 4 for complex64 (16 elements = 32 registers), 3 for complex128.
+// B = index of the step's matrix in g_chain_const.
 template <typename R, int NL, int MASK>
-__device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
-                                           const typename StageB<R>::type *__restrict__ B)
+__device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL], const int B)
 {
     using C = typename Cplx<R>::type;
     constexpr int LK = ((MASK >> 0) & 1) + ((MASK >> 1) & 1) + ((MASK >> 2) & 1) + ((MASK >> 3) & 1);
@@ -238,13 +261,13 @@ __device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
         for (int c = 0; c < D && c < NCH; c++)
 #pragma unroll
             for (int nn = 0; nn < CH; nn++)
-                ring[c][nn] = B[(c / CPR) * NP + (c % CPR) * CH + nn];
+                ring[c][nn] = ConstB<R>(B + (c / CPR) * NP + (c % CPR) * CH + nn);
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             if (c + D < NCH) {
 #pragma unroll
                 for (int nn = 0; nn < CH; nn++)
-                    ring[(c + D) % (D + 1)][nn] = B[((c + D) / CPR) * NP + ((c + D) % CPR) * CH + nn];
+                    ring[(c + D) % (D + 1)][nn] = ConstB<R>(B + ((c + D) / CPR) * NP + ((c + D) % CPR) * CH + nn);
             }
             const int k = c / CPR, n0 = (c % CPR) * CH;
 #pragma unroll
@@ -276,7 +299,7 @@ __device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
                 const C a = E[g | Spread<MASK>(k)];
 #pragma unroll
                 for (int n = 0; n < K; n++)
-                    CMulAdd(acc[n], a, B[k * NP + n]);
+                    CMulAdd(acc[n], a, ConstB<R>(B + k * NP + n));
             }
 #pragma unroll
             for (int n = 0; n < K; n++)
@@ -286,8 +309,7 @@ __device__ __forceinline__ void ApplyLocal(typename Cplx<R>::type (&E)[1 << NL],
 }
 
 template <typename R, int NL>
-__device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1 << NL],
-                                                   const typename StageB<R>::type *__restrict__ B,
+__device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1 << NL], const int B,
                                                    const int mask)
 {
     if constexpr (NL == 4) {
@@ -323,8 +345,7 @@ __device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1
 
 template <typename R>
 __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__restrict__ tile,
-                                                   const typename StageB<R>::type *__restrict__ Bs,
-                                                   const ChainStageParams &g,
+                                                   const int const_base, const ChainStageParams &g,
                                                    const uint16_t *__restrict__ gtab,
                                                    const unsigned a_tid, const int tid)
 {
@@ -356,7 +377,7 @@ __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__res
         for (int t = 0; t < count; t++) {
             const unsigned cur = desc;
             desc = g.desc[(t + 1) & (kChainMaxStageSteps - 1)];
-            ApplyLocalDispatch<R, NL>(E, Bs + (cur >> 8), static_cast<int>(cur & 0xffu));
+            ApplyLocalDispatch<R, NL>(E, const_base + static_cast<int>(cur >> 8), static_cast<int>(cur & 0xffu));
         }
 #pragma unroll
         for (int e = 0; e < NE; e++)
@@ -394,8 +415,6 @@ template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems)
     using C = typename Cplx<R>::type;
     size_t b = sizeof(C) * kChainBuffers * (size_t(1) << log_tile);
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
-    if (sizeof(R) == 4)
-        b += sizeof(float4) * static_cast<size_t>(resident_elems);
     b += sizeof(uint16_t) * kChainMaxSteps * kChainThreads; // per-thread stage offsets
     return b;
 }
@@ -411,16 +430,7 @@ __global__ void __launch_bounds__(kChainCtaThreads, 1)
     C *tiles = reinterpret_cast<C *>(chain_smem);
     const int tile_elems = 1 << p.log_tile;
     C *Bm = tiles + kChainBuffers * tile_elems;
-    // complex64: a second copy of the matrices in the packed-FMA form used by the register stages
-    typename StageB<R>::type *Bs = reinterpret_cast<typename StageB<R>::type *>(Bm);
-    uint16_t *atid;
-    if constexpr (sizeof(R) == 4) {
-        Bs = reinterpret_cast<float4 *>(Bm + ((p.resident_elems + 1) & ~1));
-        atid = reinterpret_cast<uint16_t *>(Bs + p.resident_elems);
-    }
-    else {
-        atid = reinterpret_cast<uint16_t *>(Bm + ((p.resident_elems + 1) & ~1));
-    }
+    uint16_t *atid = reinterpret_cast<uint16_t *>(Bm + ((p.resident_elems + 1) & ~1));
     const int tid = threadIdx.x;
 
     // per-thread part of every stage's tile address (tile independent): one table lookup per stage
@@ -448,8 +458,6 @@ __global__ void __launch_bounds__(kChainCtaThreads, 1)
             if (static_cast<int>(n) < N)
                 v = __ldg(Rs + (Deposit(k, q.rk, q.log_k) | Deposit(n, q.rn, q.log_n)));
             Bm[q.b_off + e] = v;
-            if constexpr (sizeof(R) == 4)
-                Bs[q.b_off + e] = make_float4(v.x, v.y, -v.y, v.x);
         }
     }
     __syncthreads();
@@ -469,7 +477,7 @@ __global__ void __launch_bounds__(kChainCtaThreads, 1)
                 const ChainStageParams &g = p.stage[sg];
                 const unsigned a_tid = atid[sg * kChainThreads + tid];
                 if (g.kind == 1) {
-                    ChainRegisterStage<R>(tile, Bs, g, p.stage_tab[sg], a_tid, tid);
+                    ChainRegisterStage<R>(tile, p.const_base, g, p.stage_tab[sg], a_tid, tid);
                 }
                 else {
                     const ChainStepParams &q = p.step[g.first];
@@ -589,11 +597,54 @@ __global__ void __launch_bounds__(kChainCtaThreads, 1)
     }
 }
 
+// Small operands -> staging buffer, as K x np matrices in the form the register stages read from the
+// constant bank: complex64 (b.x, b.y, -b.y, b.x), complex128 (b.x, b.y); columns n >= N are zero.
 template <typename R>
-int LaunchChainT(const ChainParams &p, const ChainPtrs &ptrs, const void *x0, void *xk,
+__global__ void __launch_bounds__(256)
+    ChainGatherKernel(const __grid_constant__ ChainParams p, const __grid_constant__ ChainPtrs rp,
+                      uint4 *__restrict__ staging)
+{
+    using C = typename Cplx<R>::type;
+    for (int s = blockIdx.x; s < p.n_steps; s += gridDim.x) {
+        const ChainStepParams &q = p.step[s];
+        const C *Rs = static_cast<const C *>(rp.r[s]);
+        const int np = q.np;
+        const int N = 1 << q.log_n;
+        const int total = np << q.log_k;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const unsigned k = e / np, n = e % np;
+            C v = C{R(0), R(0)};
+            if (static_cast<int>(n) < N)
+                v = __ldg(Rs + (Deposit(k, q.rk, q.log_k) | Deposit(n, q.rn, q.log_n)));
+            uint4 w;
+            if constexpr (sizeof(R) == 4) {
+                w = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(-v.y),
+                               __float_as_uint(v.x));
+            }
+            else {
+                w = make_uint4(static_cast<unsigned>(__double2loint(v.x)), static_cast<unsigned>(__double2hiint(v.x)),
+                               static_cast<unsigned>(__double2loint(v.y)), static_cast<unsigned>(__double2hiint(v.y)));
+            }
+            staging[q.b_off + e] = w;
+        }
+    }
+}
+
+template <typename R>
+int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk, void *staging, int slot,
                  cudaStream_t stream)
 {
     using C = typename Cplx<R>::type;
+    JB_REQUIRE(slot >= 0 && slot < kChainConstSlots && staging != nullptr, "chain: no constant-bank slot");
+    JB_REQUIRE(p.resident_elems <= kChainConstEntries, "chain: too many matrix entries");
+    p.const_base = slot * kChainConstEntries;
+    ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(staging));
+    JB_CUDA(cudaGetLastError());
+    void *sym = nullptr;
+    JB_CUDA(cudaGetSymbolAddress(&sym, g_chain_const));
+    JB_CUDA(cudaMemcpyAsync(static_cast<uint4 *>(sym) + p.const_base, staging,
+                            sizeof(uint4) * static_cast<size_t>(p.resident_elems), cudaMemcpyDeviceToDevice,
+                            stream));
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems);
     auto kernel = ChainKernel<R>;
     if (smem > 48 * 1024)
@@ -748,6 +799,10 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
             *why = "shared memory";
             return 1;
         }
+        if (lay.params.resident_elems > kChainConstEntries) {
+            *why = "too many matrix entries";
+            return 1;
+        }
     }
     // the bit-level replay must agree with the index-level one
     {
@@ -773,7 +828,37 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     return 0;
 }
 
-int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk,
+size_t ChainStagingBytes() { return sizeof(uint4) * kChainConstEntries; }
+
+// constant-bank slots: [0, kChainConstSlots - 1) for plans, the last one for operator-level calls
+namespace {
+std::mutex g_slot_mutex;
+bool g_slot_used[64][kChainConstSlots];
+} // namespace
+
+int ChainAcquireSlot(int device)
+{
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    if (device < 0 || device >= 64)
+        return -1;
+    for (int s = 0; s < kChainConstSlots - 1; s++)
+        if (!g_slot_used[device][s]) {
+            g_slot_used[device][s] = true;
+            return s;
+        }
+    return -1;
+}
+
+void ChainReleaseSlot(int device, int slot)
+{
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    if (device >= 0 && device < 64 && slot >= 0 && slot < kChainConstSlots - 1)
+        g_slot_used[device][slot] = false;
+}
+
+int ChainOperatorSlot() { return kChainConstSlots - 1; }
+
+int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, void *staging, int slot,
                 cudaStream_t stream)
 {
     ChainParams p;
@@ -784,8 +869,8 @@ int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *x
     for (int s = 0; s < op.n_steps; s++)
         ptrs.r[s] = r[s];
     if (op.dtype == JB_C64)
-        return LaunchChainT<float>(p, ptrs, x0, xk, stream);
-    return LaunchChainT<double>(p, ptrs, x0, xk, stream);
+        return LaunchChainT<float>(p, ptrs, x0, xk, staging, slot, stream);
+    return LaunchChainT<double>(p, ptrs, x0, xk, staging, slot, stream);
 }
 
 } // namespace jb

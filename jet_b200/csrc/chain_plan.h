@@ -68,6 +68,8 @@ struct ChainParams {
     int32_t log_tile_out; // tile bits alive when the tile is stored
     int32_t log_outer;
     int32_t resident_elems; // total elements of the resident area
+    int32_t const_base;     // first entry of this launch's matrices in the constant bank (set at launch)
+    int32_t pad0;
     long long n_tiles;
     uint16_t in_scol[kChainMaxTileBits];  // tile address column of load-index bit q
     uint16_t out_scol[kChainMaxTileBits]; // tile address column of store-index bit q

@@ -216,7 +216,8 @@ struct jb_plan {
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0;
     size_t ws_off = 0, ws_bytes = 0;
-    size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0;
+    size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0, chain_stage_off = 0;
+    int chain_slot = -1; // constant-bank slot of the fused chains (-1: none, fusion off)
     int64_t store_cap = 0, list_cap = 0;
     int64_t result_elems = 1;
     int result_node = -1;
@@ -242,7 +243,8 @@ int LaunchOp(jb_plan *p, const Op &op)
         for (size_t i = 0; i < op.r_nodes.size(); i++)
             r[i] = p->arena + p->nodes[op.r_nodes[i]].offset;
         return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r,
-                           p->arena + p->nodes[op.out].offset, p->stream);
+                           p->arena + p->nodes[op.out].offset, p->arena + p->chain_stage_off, p->chain_slot,
+                           p->stream);
     }
     const Step &st = p->steps[op.steps[0]];
     return LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
@@ -484,7 +486,12 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
 
     // ---- per-slice launch units: fuse runs of "large tensor absorbs a small tensor" steps ----------
     {
-        const bool fuse = !keep && !(d->flags & JB_PLAN_NO_FUSE) && ChainFusionEnabled();
+        bool fuse = !keep && !(d->flags & JB_PLAN_NO_FUSE) && ChainFusionEnabled();
+        if (fuse) {
+            // the chains' step matrices go through a constant-bank slot owned by the plan
+            p->chain_slot = ChainAcquireSlot(p->device);
+            fuse = p->chain_slot >= 0;
+        }
         std::vector<int> consumer(p->nodes.size(), -1);
         for (size_t s = 0; s < p->steps.size(); s++) {
             consumer[p->steps[s].a] = static_cast<int>(s);
@@ -611,6 +618,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     p->list_cap = std::max<int64_t>(std::min<int64_t>(p->num_slices, kMaxListed), 1);
     p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
     p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
+    p->chain_stage_off = alloc.Alloc(ChainStagingBytes());
     for (size_t e = 0; e < exec.size(); e++) {
         Node &C = p->nodes[exec[e].out];
         C.offset = alloc.Alloc(C.elems * p->eb);
@@ -680,7 +688,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         if (op.kernel == 2) {
             S.chains++;
             S.steps_chained += static_cast<int32_t>(op.steps.size());
-            S.launches_per_slice += 1;
+            S.launches_per_slice += 2; // matrix gather + chain kernel (plus one D2D copy node)
             S.fused_bytes_per_slice += op.chain.bytes;
         }
         else {
@@ -727,6 +735,8 @@ int jb_plan_destroy(jb_plan *p)
         cudaFreeHost(p->h_list);
     if (p->arena)
         cudaFree(p->arena);
+    if (p->chain_slot >= 0)
+        ChainReleaseSlot(p->device, p->chain_slot);
     delete p;
     return 0;
 }
@@ -901,7 +911,7 @@ int jb_plan_ops(const jb_plan *p, jb_op_info_t *ops, int32_t cap, int32_t *count
         o.pad = 0;
         o.flops = o.bytes = o.step_bytes = 0.0;
         if (op.kernel == 2) {
-            o.launches = 1;
+            o.launches = 2;
             o.flops = op.chain.flops;
             o.bytes = op.chain.bytes;
             o.step_bytes = op.chain.step_bytes;
