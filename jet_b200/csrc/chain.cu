@@ -664,7 +664,12 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
 // -------------------------------------------------------------------------------------------------
 int ChainMaxTileBits(int dtype)
 {
-    return dtype == JB_C64 ? 13 : 12; // 64 KiB of shared memory per CTA either way
+    // 64 KiB of shared memory per tile buffer either way; JB_CHAIN_TILE_BITS lowers it (experiments)
+    static const int cap = [] {
+        const char *e = getenv("JB_CHAIN_TILE_BITS");
+        return e ? atoi(e) : 99;
+    }();
+    return std::min(cap, dtype == JB_C64 ? 13 : 12);
 }
 
 bool ChainFusionEnabled()
