@@ -29,9 +29,6 @@ static_assert(sizeof(ChainParams) + sizeof(ChainPtrs) <= 4000, "kernel parameter
 
 namespace {
 
-constexpr int kLogChainThreads = kChainLogThreads;
-constexpr int kChainThreads = 1 << kLogChainThreads;
-
 template <typename R> struct Cplx;
 template <> struct Cplx<float> {
     using type = float2;
@@ -93,7 +90,7 @@ __device__ __forceinline__ unsigned long long Deposit(unsigned long long idx, co
 // One contraction step applied in place to the tile.  A "group" is one assignment of the tile bits
 // the step does not contract; its K inputs are read into registers, the N outputs are written to
 // the positions of the new bits.  KC = K (all k values in registers), G = groups in flight.
-template <typename R, int KC, int G>
+template <typename R, int KC, int G, int LOGT>
 __device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ tile,
                                           const typename Cplx<R>::type *__restrict__ Bm,
                                           const ChainStepParams &q,
@@ -124,7 +121,7 @@ __device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ t
     const unsigned ncol3 = log_n >= 4 ? q.ncol[3] : 0u;
 
     const bool t_ok = tid < (1 << log_g);
-    const int per_thread = log_g > kLogChainThreads ? (1 << (log_g - kLogChainThreads)) : 1;
+    const int per_thread = log_g > LOGT ? (1 << (log_g - LOGT)) : 1;
     const C *bbase = Bm + q.b_off;
 
     for (int j0 = 0; j0 < per_thread; j0 += G) {
@@ -343,35 +340,39 @@ __device__ __forceinline__ void ApplyLocalDispatch(typename Cplx<R>::type (&E)[1
     }
 }
 
-template <typename R>
-__device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__restrict__ tile,
-                                                   const int const_base, const ChainStageParams &g,
+// Shared-memory addresses are BYTE offsets into the tile: the address of register-tile element e is
+// tile + ((thread part ^ table part) ^ local part(e)) — one three-input XOR per element, the tile base
+// rides in the load's uniform-register operand.
+template <typename R, int LOGT>
+__device__ __forceinline__ void ChainRegisterStage(unsigned char *__restrict__ tile, const int const_base,
+                                                   const ChainStageParams &g,
                                                    const uint16_t *__restrict__ gtab,
                                                    const unsigned a_tid, const int tid)
 {
     using C = typename Cplx<R>::type;
     constexpr int NL = sizeof(R) == 4 ? 4 : 3;
     constexpr int NE = 1 << NL;
+    constexpr unsigned SH = sizeof(C) == 8 ? 3 : 4;
     const int log_g = g.log_g;
     if (tid >= (1 << log_g))
         return;
-    const int per_thread = log_g > kLogChainThreads ? (1 << (log_g - kLogChainThreads)) : 1;
+    const int per_thread = log_g > LOGT ? (1 << (log_g - LOGT)) : 1;
     const int count = g.count;
     unsigned l01[4], l23[4];
     l01[0] = 0;
-    l01[1] = g.lcol[0];
-    l01[2] = g.lcol[1];
+    l01[1] = static_cast<unsigned>(g.lcol[0]) << SH;
+    l01[2] = static_cast<unsigned>(g.lcol[1]) << SH;
     l01[3] = l01[1] ^ l01[2];
     l23[0] = 0;
-    l23[1] = g.lcol[2];
-    l23[2] = NL == 4 ? g.lcol[3] : 0u;
+    l23[1] = static_cast<unsigned>(g.lcol[2]) << SH;
+    l23[2] = NL == 4 ? static_cast<unsigned>(g.lcol[3]) << SH : 0u;
     l23[3] = l23[1] ^ l23[2];
     for (int j = 0; j < per_thread; j++) {
-        const unsigned base = a_tid ^ gtab[j];
+        const unsigned base = (a_tid ^ gtab[j]) << SH;
         C E[NE];
 #pragma unroll
         for (int e = 0; e < NE; e++)
-            E[e] = tile[base ^ l01[e & 3] ^ l23[e >> 2]];
+            E[e] = *reinterpret_cast<const C *>(tile + (base ^ l01[e & 3] ^ l23[e >> 2]));
         // the descriptor of step t + 1 is fetched while step t computes
         unsigned desc = g.desc[0];
         for (int t = 0; t < count; t++) {
@@ -381,25 +382,57 @@ __device__ __forceinline__ void ChainRegisterStage(typename Cplx<R>::type *__res
         }
 #pragma unroll
         for (int e = 0; e < NE; e++)
-            tile[base ^ l01[e & 3] ^ l23[e >> 2]] = E[e];
+            *reinterpret_cast<C *>(tile + (base ^ l01[e & 3] ^ l23[e >> 2])) = E[e];
     }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-// One persistent 512-thread CTA per SM, warp-specialised over a ring of three tile buffers:
-//   warps 0-7   compute: apply the chain to tile i in place, stage by stage (FMA pipe only — these
-//               warps never touch global memory);
-//   warps 8-11  load:    cp.async tile i+1 / i+2 from X_0 into a free buffer;
-//   warps 12-15 store:   write tile i-1 from its buffer to X_k.
-// The memory warps absorb the LSU back-pressure of the 64 KB tile transfers, so the HBM traffic of two
-// tiles is in flight while the FMA pipe works on a third.  Hand-off is by named barriers
-// (bar.arrive by the producer, bar.sync by the consumer): full[b] load -> compute, done[b] compute ->
-// store, free[b] store -> load.
+// One persistent CTA per SM, warp-specialised over a ring of three tile buffers:
+//   compute warps (16 for complex64, 8 for complex128): apply the chain to tile i in place, stage by
+//               stage (FMA pipe only — these warps never touch global memory).  Four compute warps per
+//               scheduler keep the FMA pipe fed while others are between phases;
+//   2 load warps:  cp.async tile i+1 / i+2 from X_0 into a free buffer;
+//   2 store warps: write tile i-1 from its buffer to X_k, two adjacent complex64 per 16-byte store.
+// One memory warp sits on each of the four schedulers.  Their per-element address work is one XOR
+// (shared-memory side) and one 64-bit add (global side): the thread-independent halves of both maps
+// are tabulated in shared memory once per CTA.
+// Hand-off is by named barriers (bar.arrive by the producer, bar.sync by the consumer): full[b]
+// load -> compute, done[b] compute -> store, free[b] store -> load.
 constexpr int kChainBuffers = 3;
-constexpr int kChainLoadThreads = 128;
-constexpr int kChainStoreThreads = 128;
-constexpr int kChainCtaThreads = kChainThreads + kChainLoadThreads + kChainStoreThreads;
-constexpr int kBarCompute = 1, kBarFull = 2, kBarDone = 5, kBarFree = 8;
+constexpr int kChainLoadThreads = 64;
+constexpr int kChainStoreThreads = 64;
+constexpr int kChainMemThreads = kChainLoadThreads + kChainStoreThreads;
+constexpr int kChainMemTabLen = 1 << (kChainMaxTileBits - kChainMemLogLanes);
+static_assert(kChainLoadThreads == (1 << kChainMemLogLanes) && kChainStoreThreads == (1 << kChainMemLogLanes),
+              "memory warps: one thread per lane of the tile walk");
+constexpr int kBarFull = 2, kBarDone = 5, kBarFree = 8, kBarCompute = 11; // kBarCompute + group
+
+struct __align__(16) ChainMemEntry {
+    unsigned long long g; // byte offset in X_0 / X_k
+    unsigned s;           // byte offset in the tile (XORed into the thread's)
+    unsigned pad;
+};
+
+template <typename R> struct ChainCfg {
+    // a compute GROUP works on one tile: 2^kLogThreads threads (== ChainLogThreads in the planner).
+    // complex64 runs two groups on two different tiles, so that one group's FMA phases overlap the
+    // other's shared-memory phases and barriers; complex128 has the registers for one group only.
+    static constexpr int kLogThreads = 8;
+    static constexpr int kGroups = sizeof(R) == 4 ? 2 : 1;
+    static constexpr int kGroupThreads = 1 << kLogThreads;
+    static constexpr int kComputeThreads = kGroups * kGroupThreads;
+    static constexpr int kCtaThreads = kComputeThreads + kChainMemThreads;
+};
+static_assert(ChainCfg<float>::kLogThreads == ChainLogThreads(8) && ChainCfg<double>::kLogThreads == ChainLogThreads(16),
+              "planner and kernel must agree on the compute thread count");
+
+template <size_t BYTES> __device__ __forceinline__ void CpAsyncElem(unsigned dst, const unsigned char *g)
+{
+    if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
+    else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+}
 
 __device__ __forceinline__ void BarSync(int id, int count)
 {
@@ -410,49 +443,80 @@ __device__ __forceinline__ void BarArrive(int id, int count)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems)
+template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, int n_stages)
 {
     using C = typename Cplx<R>::type;
+    const int ct = ChainCfg<R>::kGroupThreads;
     size_t b = sizeof(C) * kChainBuffers * (size_t(1) << log_tile);
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
-    b += sizeof(uint16_t) * kChainMaxSteps * kChainThreads; // per-thread stage offsets
+    b += sizeof(ChainMemEntry) * 2 * kChainMemTabLen;           // load / store tables
+    b += sizeof(uint16_t) * static_cast<size_t>(n_stages) * ct; // per-thread stage offsets
     return b;
 }
 
 template <typename R>
-__global__ void __launch_bounds__(kChainCtaThreads, 1)
+__global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
     ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
                 typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
                 const __grid_constant__ ChainPtrs rp)
 {
     using C = typename Cplx<R>::type;
+    constexpr int LOGT = ChainCfg<R>::kLogThreads;
+    constexpr int GT = 1 << LOGT;                      // threads of one compute group
+    constexpr int NG = ChainCfg<R>::kGroups;           // compute groups (tiles in flight in the FMA pipe)
+    constexpr int CT = ChainCfg<R>::kComputeThreads;   // all compute threads
+    constexpr int ML = kChainMemLogLanes;
+    // complex64: a store thread owns two X_k-adjacent elements (store-index bit 0) -> 16-byte stores
+    constexpr int PAIR = sizeof(C) == 8 ? 1 : 0;
     extern __shared__ __align__(16) unsigned char chain_smem[];
     C *tiles = reinterpret_cast<C *>(chain_smem);
     const int tile_elems = 1 << p.log_tile;
     C *Bm = tiles + kChainBuffers * tile_elems;
-    uint16_t *atid = reinterpret_cast<uint16_t *>(Bm + ((p.resident_elems + 1) & ~1));
+    ChainMemEntry *tab_in = reinterpret_cast<ChainMemEntry *>(Bm + ((p.resident_elems + 1) & ~1));
+    ChainMemEntry *tab_out = tab_in + kChainMemTabLen;
+    uint16_t *atid = reinterpret_cast<uint16_t *>(tab_out + kChainMemTabLen);
     const int tid = threadIdx.x;
+    const bool pair = PAIR && p.log_tile_out >= 1;
+    const int out_bits = p.log_tile_out - (pair ? 1 : 0); // store-index bits walked by lanes and table
 
-    // per-thread part of every stage's tile address (tile independent): one table lookup per stage
-    // instead of a bit loop over kernel parameters in the hot path
-    if (tid < kChainThreads) {
+    if (tid < GT) {
+        // per-thread part of every stage's tile address (tile independent): one table lookup per stage
+        // instead of a bit loop over kernel parameters in the hot path
         for (int sg = 0; sg < p.n_stages; sg++) {
             const ChainStageParams &g = p.stage[sg];
             const uint16_t *gc = g.kind == 1 ? g.gcol : p.step[g.first].gcol;
             const int lg = g.kind == 1 ? g.log_g : p.step[g.first].log_g;
-            atid[sg * kChainThreads + tid] =
-                static_cast<uint16_t>(Lin(tid, gc, lg < kLogChainThreads ? lg : kLogChainThreads));
+            atid[sg * GT + tid] = static_cast<uint16_t>(Lin(tid, gc, lg < LOGT ? lg : LOGT));
         }
     }
 
-    // resident operands -> shared memory as K x np matrices (columns n >= N are zero)
+    else if (tid >= CT) {
+        // thread-independent halves of the load / store index maps (index bits above the lane)
+        for (int e = tid - CT; e < kChainMemTabLen; e += kChainMemThreads) {
+            const int ib = max(0, p.log_tile_in - ML - 3), ob = max(0, out_bits - ML);
+            ChainMemEntry a{0ull, 0u, 0u}, b{0ull, 0u, 0u};
+            if (e < (1 << ib)) {
+                a.g = Deposit(e, p.in_gbit + ML + 3, ib) * sizeof(C);
+                a.s = Lin(e, p.in_scol + ML + 3, ib) * static_cast<unsigned>(sizeof(C));
+            }
+            if (e < (1 << ob)) {
+                b.g = Deposit(e, p.out_gbit + ML + (pair ? 1 : 0), ob) * sizeof(C);
+                b.s = Lin(e, p.out_scol + ML + (pair ? 1 : 0), ob) * static_cast<unsigned>(sizeof(C));
+            }
+            tab_in[e] = a;
+            tab_out[e] = b;
+        }
+    }
+
+    // resident operands -> shared memory as K x np matrices (columns n >= N are zero): the matrices
+    // of the steps that run through the generic shared-memory path
     for (int s = 0; s < p.n_steps; s++) {
         const ChainStepParams &q = p.step[s];
         const C *Rs = static_cast<const C *>(rp.r[s]);
         const int np = q.np;
         const int N = 1 << q.log_n;
         const int total = np << q.log_k;
-        for (int e = tid; e < total; e += kChainCtaThreads) {
+        for (int e = tid; e < total; e += ChainCfg<R>::kCtaThreads) {
             const unsigned k = e / np, n = e % np;
             C v = C{R(0), R(0)};
             if (static_cast<int>(n) < N)
@@ -462,88 +526,100 @@ __global__ void __launch_bounds__(kChainCtaThreads, 1)
     }
     __syncthreads();
 
-    const long long n_my = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x; // tiles of this CTA
-    constexpr int kFullCount = kChainLoadThreads + kChainThreads;
-    constexpr int kDoneCount = kChainThreads + kChainStoreThreads;
+    const int n_my = static_cast<int>((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles of this CTA
+    constexpr int kFullCount = kChainLoadThreads + GT;
+    constexpr int kDoneCount = GT + kChainStoreThreads;
     constexpr int kFreeCount = kChainStoreThreads + kChainLoadThreads;
+    const unsigned tiles_s = static_cast<unsigned>(__cvta_generic_to_shared(tiles));
+    const unsigned tile_bytes = static_cast<unsigned>(tile_elems * sizeof(C));
 
-    if (tid < kChainThreads) {
+    if (tid < CT) {
         // ================================ compute warps =========================================
-        for (long long i = 0; i < n_my; i++) {
-            const int b = static_cast<int>(i % kChainBuffers);
+        // group gi takes tiles gi, gi + NG, ... of this CTA; tile i lives in buffer i % kChainBuffers
+        const int gi = tid >> LOGT;
+        const int gt = tid & (GT - 1);
+        for (int i = gi; i < n_my; i += NG) {
+            const int b = i % kChainBuffers;
             C *tile = tiles + b * tile_elems;
             BarSync(kBarFull + b, kFullCount);
             for (int sg = 0; sg < p.n_stages; sg++) {
                 const ChainStageParams &g = p.stage[sg];
-                const unsigned a_tid = atid[sg * kChainThreads + tid];
+                const unsigned a_tid = atid[sg * GT + gt];
                 if (g.kind == 1) {
-                    ChainRegisterStage<R>(tile, p.const_base, g, p.stage_tab[sg], a_tid, tid);
+                    ChainRegisterStage<R, LOGT>(reinterpret_cast<unsigned char *>(tile), p.const_base, g,
+                                                p.stage_tab[sg], a_tid, gt);
                 }
                 else {
                     const ChainStepParams &q = p.step[g.first];
                     constexpr bool kF = sizeof(R) == 4;
                     switch (q.log_k) {
                     case 0:
-                        ChainStep<R, 1, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        ChainStep<R, 1, kF ? 4 : 2, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
                         break;
                     case 1:
-                        ChainStep<R, 2, kF ? 4 : 2>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        ChainStep<R, 2, kF ? 4 : 2, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
                         break;
                     case 2:
-                        ChainStep<R, 4, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        ChainStep<R, 4, kF ? 2 : 1, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
                         break;
                     case 3:
-                        ChainStep<R, 8, kF ? 2 : 1>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        ChainStep<R, 8, kF ? 2 : 1, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
                         break;
                     default:
-                        ChainStep<R, 16, 1>(tile, Bm, q, p.stage_tab[sg], a_tid, tid);
+                        ChainStep<R, 16, 1, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
                         break;
                     }
                 }
                 if (sg + 1 < p.n_stages)
-                    BarSync(kBarCompute, kChainThreads);
+                    BarSync(kBarCompute + gi, GT);
             }
             BarArrive(kBarDone + b, kDoneCount);
         }
     }
-    else if (tid < kChainThreads + kChainLoadThreads) {
+    else if (tid < CT + kChainLoadThreads) {
         // ================================== load warps ===========================================
-        // X_0 tile -> shared memory, coalesced along the low X_0 address bits.  Each thread plays two
-        // of the 256 load lanes the index tables are built for.
-        const int lt = tid - kChainThreads;
-        const int tid_bits = min(p.log_tile_in, kLogChainThreads);
-        const int iters = p.log_tile_in > kLogChainThreads ? 1 << (p.log_tile_in - kLogChainThreads) : 1;
-        unsigned s_lane[2];
-        unsigned long long g_lane[2];
-        bool ok[2];
+        // X_0 tile -> shared memory, coalesced along the low X_0 address bits.  Load index = lane (ML
+        // bits) | jl (3 bits, offsets in registers) | jh (offsets in the shared-memory table): the
+        // inner loop is XOR + 64-bit add + cp.async per element.
+        const int lt = tid - CT;
+        const int lane_bits = min(p.log_tile_in, ML);
+        const int in_bits = max(0, min(p.log_tile_in - ML, 3));
+        const int inner_n = 1 << in_bits;
+        const int outer_n = p.log_tile_in > ML + 3 ? 1 << (p.log_tile_in - ML - 3) : 1;
+        const unsigned s_lane = Lin(lt, p.in_scol, lane_bits) * static_cast<unsigned>(sizeof(C));
+        const unsigned long long g_lane = Deposit(lt, p.in_gbit, lane_bits) * sizeof(C);
+        unsigned sl[8];
+        unsigned long long gl[8];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int v = lt + h * kChainLoadThreads;
-            s_lane[h] = Lin(v, p.in_scol, tid_bits);
-            g_lane[h] = Deposit(v, p.in_gbit, tid_bits);
-            ok[h] = v < (1 << p.log_tile_in);
+        for (int jl = 0; jl < 8; jl++) {
+            sl[jl] = Lin(jl, p.in_scol + ML, in_bits) * static_cast<unsigned>(sizeof(C));
+            gl[jl] = Deposit(jl, p.in_gbit + ML, in_bits) * sizeof(C);
         }
-        const unsigned tiles_s = static_cast<unsigned>(__cvta_generic_to_shared(tiles));
-        for (long long i = 0; i < n_my; i++) {
-            const int b = static_cast<int>(i % kChainBuffers);
+        const bool ok = lt < (1 << p.log_tile_in);
+        for (int i = 0; i < n_my; i++) {
+            const int b = i % kChainBuffers;
             const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(i) * gridDim.x;
-            const unsigned long long base = Deposit(t, p.outer_in, p.log_outer);
+            const unsigned long long base = Deposit(t, p.outer_in, p.log_outer) * sizeof(C);
             if (i >= kChainBuffers)
                 BarSync(kBarFree + b, kFreeCount);
-            const unsigned buf_s = tiles_s + static_cast<unsigned>(b * tile_elems * sizeof(C));
+            const unsigned buf_s = tiles_s + static_cast<unsigned>(b) * tile_bytes;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(X0) + (base + g_lane);
+            if (ok) {
+                if (p.log_tile_in >= ML + 3) {
+                    for (int jh = 0; jh < outer_n; jh++) {
+                        const ChainMemEntry e = tab_in[jh];
+                        const unsigned so = s_lane ^ e.s;
+                        const unsigned char *gp = src + e.g;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (!ok[h])
-                    continue;
-                const C *src = X0 + (base | g_lane[h]);
-#pragma unroll 4
-                for (int j = 0; j < iters; j++) {
-                    const unsigned dst = buf_s + (s_lane[h] ^ p.in_stab[j]) * static_cast<unsigned>(sizeof(C));
-                    const C *g = src + p.in_gtab[j];
-                    if constexpr (sizeof(C) == 8)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
-                    else
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+                        for (int jl = 0; jl < 8; jl++)
+                            CpAsyncElem<sizeof(C)>(buf_s + (so ^ sl[jl]), gp + gl[jl]);
+                    }
+                }
+                else { // tiny tiles
+                    for (int jl = 0; jl < inner_n; jl++)
+                        CpAsyncElem<sizeof(C)>(
+                            buf_s + (s_lane ^ (Lin(jl, p.in_scol + ML, in_bits) * static_cast<unsigned>(sizeof(C)))),
+                            src + Deposit(jl, p.in_gbit + ML, in_bits) * sizeof(C));
                 }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
@@ -554,41 +630,40 @@ __global__ void __launch_bounds__(kChainCtaThreads, 1)
     else {
         // ================================== store warps ==========================================
         // shared memory -> X_k tile, coalesced along the low X_k address bits
-        const int lt = tid - kChainThreads - kChainLoadThreads;
-        const int tid_bits = min(p.log_tile_out, kLogChainThreads);
-        const int iters = p.log_tile_out > kLogChainThreads ? 1 << (p.log_tile_out - kLogChainThreads) : 1;
-        unsigned s_lane[2];
-        unsigned long long g_lane[2];
-        bool ok[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int v = lt + h * kChainStoreThreads;
-            s_lane[h] = Lin(v, p.out_scol, tid_bits);
-            g_lane[h] = Deposit(v, p.out_gbit, tid_bits);
-            ok[h] = v < (1 << p.log_tile_out);
-        }
-        for (long long i = 0; i < n_my; i++) {
-            const int b = static_cast<int>(i % kChainBuffers);
+        const int lt = tid - CT - kChainLoadThreads;
+        const int lane_bits = min(out_bits, ML);
+        const int iters = out_bits > ML ? 1 << (out_bits - ML) : 1;
+        const int sh = pair ? 1 : 0;
+        const unsigned s_lane = Lin(lt, p.out_scol + sh, lane_bits) * static_cast<unsigned>(sizeof(C));
+        const unsigned s_pair = pair ? p.out_scol[0] * static_cast<unsigned>(sizeof(C)) : 0u;
+        const unsigned long long g_lane = Deposit(lt, p.out_gbit + sh, lane_bits) * sizeof(C);
+        const bool ok = lt < (1 << out_bits);
+        for (int i = 0; i < n_my; i++) {
+            const int b = i % kChainBuffers;
             const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(i) * gridDim.x;
-            const unsigned long long base = Deposit(t, p.outer_out, p.log_outer);
-            const C *buf = tiles + b * tile_elems;
+            const unsigned long long base = Deposit(t, p.outer_out, p.log_outer) * sizeof(C);
+            const unsigned char *buf = reinterpret_cast<const unsigned char *>(tiles) + static_cast<size_t>(b) * tile_bytes;
+            unsigned char *dst = reinterpret_cast<unsigned char *>(Xk) + (base + g_lane);
             BarSync(kBarDone + b, kDoneCount);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (!ok[h])
-                    continue;
-                C *dst = Xk + (base | g_lane[h]);
-                constexpr int U = 8;
-                for (int j0 = 0; j0 < iters; j0 += U) {
-                    C v[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (j0 + u < iters)
-                            v[u] = buf[s_lane[h] ^ p.out_stab[j0 + u]];
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (j0 + u < iters)
-                            dst[p.out_gtab[j0 + u]] = v[u];
+            if (ok) {
+                if (pair) {
+                    if constexpr (PAIR) {
+#pragma unroll 4
+                        for (int j = 0; j < iters; j++) {
+                            const ChainMemEntry e = tab_out[j];
+                            const unsigned so = s_lane ^ e.s;
+                            const float2 v0 = *reinterpret_cast<const float2 *>(buf + so);
+                            const float2 v1 = *reinterpret_cast<const float2 *>(buf + (so ^ s_pair));
+                            *reinterpret_cast<float4 *>(dst + e.g) = make_float4(v0.x, v0.y, v1.x, v1.y);
+                        }
+                    }
+                }
+                else {
+#pragma unroll 4
+                    for (int j = 0; j < iters; j++) {
+                        const ChainMemEntry e = tab_out[j];
+                        *reinterpret_cast<C *>(dst + e.g) = *reinterpret_cast<const C *>(buf + (s_lane ^ e.s));
+                    }
                 }
             }
             if (i + kChainBuffers < n_my)
@@ -645,13 +720,14 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     JB_CUDA(cudaMemcpyAsync(static_cast<uint4 *>(sym) + p.const_base, staging,
                             sizeof(uint4) * static_cast<size_t>(p.resident_elems), cudaMemcpyDeviceToDevice,
                             stream));
-    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems);
+    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages);
+    JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
     auto kernel = ChainKernel<R>;
     if (smem > 48 * 1024)
         JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(p.n_tiles, NumSMs())));
-    kernel<<<grid, kChainCtaThreads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p,
+    kernel<<<grid, ChainCfg<R>::kCtaThreads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p,
                                                      ptrs);
     JB_CUDA(cudaGetLastError());
     return 0;
@@ -797,9 +873,10 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
         !PlanChain(spec, max_tile_bits, wide - 1, &lay, why))
         return 1;
     {
-        const size_t smem = spec.elem_bytes == 8
-                                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems)
-                                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems);
+        const size_t smem =
+            spec.elem_bytes == 8
+                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages)
+                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages);
         if (smem > 227 * 1024) {
             *why = "shared memory";
             return 1;

@@ -31,8 +31,13 @@ constexpr int kChainMaxTileBits = 13;
 constexpr int kChainMaxOuterBits = 56;
 constexpr int kChainMaxLogK = 4;
 constexpr int kChainMaxLogN = 4;
-constexpr int kChainLogThreads = 8; // the kernel runs 256-thread CTAs
-constexpr int kChainTabLen = 1 << (kChainMaxTileBits - kChainLogThreads);
+// Threads of one compute group (the threads that share a tile); the kernel may run several groups
+// on different tiles, and the memory warps come on top.
+constexpr int kChainMinLogThreads = 8;
+inline constexpr int ChainLogThreads(int /*elem_bytes*/) { return 8; }
+constexpr int kChainTabLen = 1 << (kChainMaxTileBits - kChainMinLogThreads);
+// The memory warps walk a tile with 2^kChainMemLogLanes lanes (bits above are a per-CTA table).
+constexpr int kChainMemLogLanes = 6;
 
 struct ChainStepParams {
     uint8_t log_k, log_n, log_g, pad0;
@@ -69,7 +74,7 @@ struct ChainParams {
     int32_t log_outer;
     int32_t resident_elems; // total elements of the resident area
     int32_t const_base;     // first entry of this launch's matrices in the constant bank (set at launch)
-    int32_t pad0;
+    int32_t log_threads;    // compute threads per CTA = 2^log_threads (ChainLogThreads)
     long long n_tiles;
     uint16_t in_scol[kChainMaxTileBits];  // tile address column of load-index bit q
     uint16_t out_scol[kChainMaxTileBits]; // tile address column of store-index bit q
@@ -79,10 +84,8 @@ struct ChainParams {
     uint8_t outer_out[kChainMaxOuterBits]; // X_k address bit of tile-number bit q
     ChainStepParams step[kChainMaxSteps];
     ChainStageParams stage[kChainMaxSteps];
-    // thread-independent parts of the index maps, tabulated for the CTA size: entry j is the
-    // contribution of the work-index bits above the thread id (j = index >> kChainLogThreads)
-    unsigned long long in_gtab[kChainTabLen], out_gtab[kChainTabLen];
-    uint16_t in_stab[kChainTabLen], out_stab[kChainTabLen];
+    // thread-independent part of every stage's index map, tabulated for the CTA size: entry j is the
+    // contribution of the work-index bits above the thread id (j = index >> log_threads)
     uint16_t stage_tab[kChainMaxSteps][kChainTabLen];
 };
 
@@ -172,7 +175,7 @@ inline bool ChainReplay(const ChainSpec &spec, std::vector<std::vector<int>> *x_
 // tile must contain (coalescing run = 2^lane_bits elements).  Fails if the tile would exceed
 // max_tile_bits.
 inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, ChainLayout *out,
-                      std::string *why)
+                      std::string *why, int extra_quiet = 0)
 {
     using namespace chain_detail;
     std::string dummy;
@@ -218,6 +221,13 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
     for (size_t q = 0; q < x0.size() && static_cast<int>(quiet.size()) < bank_bits; q++)
         if (!touched.count(x0[q]))
             quiet.insert(x0[q]);
+    // padding: more untouched bits (lowest X_0 address bits first) make the tile larger, so that every
+    // compute thread owns a register tile in every stage
+    for (size_t q = 0; q < x0.size() && extra_quiet > 0; q++)
+        if (!touched.count(x0[q]) && !quiet.count(x0[q])) {
+            quiet.insert(x0[q]);
+            extra_quiet--;
+        }
 
     // physical tile positions
     std::map<int, int> pos;
@@ -335,9 +345,12 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
 
     // ---- swizzle: bank bits of physical position p >= bank_bits get XORed with sw[p] ---------------
     std::vector<unsigned> sw(64, 0);
+    // The store warps write X_k-adjacent PAIRS of complex64 elements (one 16-byte store): the lanes of
+    // one shared-memory read run over store-index bits 1.. instead of 0..
+    const int store_skip = spec.elem_bytes == 8 && static_cast<int>(alive.size()) > bank_bits ? 1 : 0;
     auto lane_positions = [&](const std::vector<int> &ids) {
         std::vector<int> r;
-        for (int q = 0; q < bank_bits && q < static_cast<int>(ids.size()); q++)
+        for (int q = store_skip; q < store_skip + bank_bits && q < static_cast<int>(ids.size()); q++)
             r.push_back(pos.count(ids[q]) ? pos[ids[q]] : -1);
         return r;
     };
@@ -474,19 +487,9 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
                     r ^= c[q];
             return r;
         };
-        auto dep = [](unsigned idx, const uint8_t *bit, int nbits) {
-            unsigned long long r = 0;
-            for (int q = 0; q < nbits; q++)
-                r |= static_cast<unsigned long long>((idx >> q) & 1u) << bit[q];
-            return r;
-        };
-        const int L = kChainLogThreads;
+        const int L = ChainLogThreads(spec.elem_bytes);
+        P.log_threads = L;
         for (int j = 0; j < kChainTabLen; j++) {
-            const int ib = std::max(0, P.log_tile_in - L), ob = std::max(0, P.log_tile_out - L);
-            P.in_gtab[j] = dep(j, P.in_gbit + L, ib);
-            P.in_stab[j] = static_cast<uint16_t>(lin(j, P.in_scol + L, ib));
-            P.out_gtab[j] = dep(j, P.out_gbit + L, ob);
-            P.out_stab[j] = static_cast<uint16_t>(lin(j, P.out_scol + L, ob));
             for (int sg = 0; sg < P.n_stages; sg++) {
                 const ChainStageParams &G = P.stage[sg];
                 const uint16_t *gc = G.kind == 1 ? G.gcol : P.step[G.first].gcol;

@@ -18,8 +18,8 @@ using namespace jb;
 using cd = std::complex<double>;
 
 namespace {
-constexpr int kLogThreads = kChainLogThreads;
-constexpr int kThreads = 1 << kLogThreads;
+constexpr int kMemLog = kChainMemLogLanes;
+constexpr int kMemThreads = 1 << kMemLog;
 
 // worst number of distinct addresses that fall into one bank group within a half/quarter warp
 int ConflictDegree(const std::vector<unsigned> &addr_by_lane, int elem_bytes)
@@ -67,6 +67,10 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
         return 1;
     }
     const ChainParams &p = lay.params;
+    const int kLogThreads = p.log_threads;
+    const int kThreads = 1 << kLogThreads;
+    if (kLogThreads != ChainLogThreads(elem_bytes))
+        return 2;
     *n_out_bits = static_cast<int>(lay.xk_bits.size());
     for (size_t q = 0; q < lay.xk_bits.size(); q++)
         out_bits[q] = lay.xk_bits[q];
@@ -86,10 +90,14 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
             Bm[q.b_off + e] = v;
         }
     }
-    const int in_tid_bits = std::min(p.log_tile_in, kLogThreads);
-    const int out_tid_bits = std::min(p.log_tile_out, kLogThreads);
-    const int in_iters = p.log_tile_in > kLogThreads ? 1 << (p.log_tile_in - kLogThreads) : 1;
-    const int out_iters = p.log_tile_out > kLogThreads ? 1 << (p.log_tile_out - kLogThreads) : 1;
+    // memory warps: 2^kMemLog lanes, the index bits above come from a per-CTA table; complex64 store
+    // threads own two X_k-adjacent elements (store-index bit 0)
+    const int pair = (elem_bytes == 8 && p.log_tile_out >= 1) ? 1 : 0;
+    const int st_bits = p.log_tile_out - pair;
+    const int in_lane_bits = std::min(p.log_tile_in, kMemLog);
+    const int out_lane_bits = std::min(st_bits, kMemLog);
+    const int in_iters = p.log_tile_in > kMemLog ? 1 << (p.log_tile_in - kMemLog) : 1;
+    const int out_iters = st_bits > kMemLog ? 1 << (st_bits - kMemLog) : 1;
     const cd poison(1e300, 1e300);
 
     for (long long t = 0; t < p.n_tiles; t++) {
@@ -98,16 +106,18 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
         std::fill(tile.begin(), tile.end(), poison);
         // load
         for (int j = 0; j < in_iters; j++) {
-            for (int w = 0; w < kThreads / 32; w++) {
+            for (int w = 0; w < kMemThreads / 32; w++) {
                 std::vector<unsigned> lanes(32, 0xffffffffu);
                 for (int l = 0; l < 32; l++) {
-                    const int tid = w * 32 + l;
-                    if (tid >= (1 << p.log_tile_in))
+                    const int lt = w * 32 + l;
+                    if (lt >= (1 << p.log_tile_in))
                         continue;
-                    const unsigned long long g = in_base | ChainDeposit(tid, p.in_gbit, in_tid_bits) |
-                                                 p.in_gtab[j];
-                    const unsigned sa = ChainLin(tid, p.in_scol, in_tid_bits) ^
-                                        p.in_stab[j];
+                    const int ib = std::max(0, p.log_tile_in - kMemLog);
+                    const unsigned long long g = in_base | ChainDeposit(lt, p.in_gbit, in_lane_bits) |
+                                                 ChainDeposit(j, p.in_gbit + kMemLog, ib);
+                    const unsigned sa = ChainLin(lt, p.in_scol, in_lane_bits) ^ ChainLin(j, p.in_scol + kMemLog, ib);
+                    if (tile[sa] != poison)
+                        hazards++; // two lanes load the same tile element
                     tile[sa] = cd(x0[2 * g], x0[2 * g + 1]);
                     lanes[l] = sa;
                 }
@@ -240,22 +250,31 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
         }
         // store
         for (int j = 0; j < out_iters; j++) {
-            for (int w = 0; w < kThreads / 32; w++) {
+            for (int w = 0; w < kMemThreads / 32; w++) {
+              for (int half = 0; half <= pair; half++) {
                 std::vector<unsigned> lanes(32, 0xffffffffu);
                 for (int l = 0; l < 32; l++) {
-                    const int tid = w * 32 + l;
-                    if (tid >= (1 << p.log_tile_out))
+                    const int lt = w * 32 + l;
+                    if (lt >= (1 << st_bits))
                         continue;
-                    const unsigned long long g = out_base | ChainDeposit(tid, p.out_gbit, out_tid_bits) |
-                                                 p.out_gtab[j];
-                    const unsigned sa = ChainLin(tid, p.out_scol, out_tid_bits) ^
-                                        p.out_stab[j];
+                    const int ob = std::max(0, st_bits - kMemLog);
+                    unsigned long long g = out_base | ChainDeposit(lt, p.out_gbit + pair, out_lane_bits) |
+                                           ChainDeposit(j, p.out_gbit + kMemLog + pair, ob);
+                    unsigned sa = ChainLin(lt, p.out_scol + pair, out_lane_bits) ^
+                                  ChainLin(j, p.out_scol + kMemLog + pair, ob);
+                    if (half) {
+                        if (p.out_gbit[0] != 0)
+                            hazards += 1000; // the pair must be X_k-adjacent
+                        g |= 1ull;
+                        sa ^= p.out_scol[0];
+                    }
                     out[2 * g] = tile[sa].real();
                     out[2 * g + 1] = tile[sa].imag();
                     lanes[l] = sa;
                 }
                 if (t == 0)
                     store_conf = std::max(store_conf, ConflictDegree(lanes, elem_bytes));
+              }
             }
         }
     }
