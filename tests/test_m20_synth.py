@@ -59,19 +59,27 @@ def test_committed_m20_file_is_reproducible():
 
 @pytest.mark.gpu
 def test_m20_slice_matches_reference_golden():
+    """Two m=20 slices against the reference engine's results on the same file (tools/make_m20_golden.py).
+    A single slice amplitude is a sum with heavy cancellation: the reference's OWN complex64 result is
+    2e-4 (slice 0) / 9e-6 (slice 12345678901) away from its complex128 result.  So: complex128 must
+    match the reference's complex128 to 1e-12 relative (the BASELINE tolerance), and complex64 must be
+    within max(1e-5, the reference's own complex64 error) of the reference's complex128 value."""
     from jet_b200 import ContractionPlan, NetworkFile
     gpath = os.path.join(DATA, "syc53_m20_seed1.golden.json")
-    if not os.path.exists(gpath):
-        pytest.skip("m=20 golden not generated")
     gold = json.load(open(gpath))
     meta = json.load(open(os.path.join(DATA, "syc53_m20_seed1.meta.json")))
-    net = NetworkFile.load(os.path.join(DATA, "syc53_m20_seed1.json"), np.complex64)
-    with ContractionPlan(net, meta["sliced_indices"], store_results=True) as plan:
-        assert plan.num_slices == 2 ** 58
-        ids = [int(k) for k in gold]
-        plan.reset()
-        plan.run_list(ids)
-        for n, k in enumerate(gold):
-            want = complex(gold[k]["re"], gold[k]["im"])
-            got = plan.slice_result(n).reshape(-1)[0]
-            assert abs(got - want) / abs(want) < 1e-5, (k, got, want)
+    ids = [int(k) for k in gold]
+    for dtype, tol in ((np.complex128, 1e-12), (np.complex64, 1e-5)):
+        net = NetworkFile.load(os.path.join(DATA, "syc53_m20_seed1.json"), dtype)
+        with ContractionPlan(net, meta["sliced_indices"], store_results=True) as plan:
+            assert plan.num_slices == 2 ** 58
+            plan.reset()
+            plan.run_list(ids)
+            for n, k in enumerate(gold):
+                truth = complex(gold[k]["re_c128"], gold[k]["im_c128"])
+                ref64 = complex(gold[k]["re"], gold[k]["im"])
+                got = complex(plan.slice_result(n).reshape(-1)[0])
+                err = abs(got - truth) / abs(truth)
+                ref_err = abs(ref64 - truth) / abs(truth)
+                bound = tol if dtype == np.complex128 else max(tol, ref_err)
+                assert err < bound, (k, dtype, got, truth, err, ref_err)
