@@ -370,9 +370,12 @@ __device__ __forceinline__ void ChainRegisterStage(unsigned char *__restrict__ t
     for (int j = 0; j < per_thread; j++) {
         const unsigned base = (a_tid ^ gtab[j]) << SH;
         C E[NE];
+        unsigned off[NE];
 #pragma unroll
-        for (int e = 0; e < NE; e++)
-            E[e] = *reinterpret_cast<const C *>(tile + (base ^ l01[e & 3] ^ l23[e >> 2]));
+        for (int e = 0; e < NE; e++) {
+            off[e] = base ^ l01[e & 3] ^ l23[e >> 2];
+            E[e] = *reinterpret_cast<const C *>(tile + off[e]);
+        }
         // the descriptor of step t + 1 is fetched while step t computes
         unsigned desc = g.desc[0];
         for (int t = 0; t < count; t++) {
@@ -382,7 +385,7 @@ __device__ __forceinline__ void ChainRegisterStage(unsigned char *__restrict__ t
         }
 #pragma unroll
         for (int e = 0; e < NE; e++)
-            *reinterpret_cast<C *>(tile + (base ^ l01[e & 3] ^ l23[e >> 2])) = E[e];
+            *reinterpret_cast<C *>(tile + off[e]) = E[e];
     }
 }
 
@@ -536,7 +539,9 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
     if (tid < CT) {
         // ================================ compute warps =========================================
         // group gi takes tiles gi, gi + NG, ... of this CTA; tile i lives in buffer i % kChainBuffers
-        const int gi = tid >> LOGT;
+        // (the shuffle tells the compiler the group index is warp-uniform: tile base, buffer index and
+        // loop counters then live in uniform registers and ride in the LDS/STS address operand)
+        const int gi = __shfl_sync(0xffffffffu, tid >> LOGT, 0);
         const int gt = tid & (GT - 1);
         for (int i = gi; i < n_my; i += NG) {
             const int b = i % kChainBuffers;
@@ -713,13 +718,20 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     JB_REQUIRE(slot >= 0 && slot < kChainConstSlots && staging != nullptr, "chain: no constant-bank slot");
     JB_REQUIRE(p.resident_elems <= kChainConstEntries, "chain: too many matrix entries");
     p.const_base = slot * kChainConstEntries;
-    ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(staging));
-    JB_CUDA(cudaGetLastError());
-    void *sym = nullptr;
-    JB_CUDA(cudaGetSymbolAddress(&sym, g_chain_const));
-    JB_CUDA(cudaMemcpyAsync(static_cast<uint4 *>(sym) + p.const_base, staging,
-                            sizeof(uint4) * static_cast<size_t>(p.resident_elems), cudaMemcpyDeviceToDevice,
-                            stream));
+    // The matrices of the register stages go straight into this launch's constant-bank slot: the
+    // bank is ordinary device memory behind the symbol's address, and a kernel boundary separates
+    // the writer from the readers (the constant cache does not outlive a launch).  Chains without a
+    // register stage (small tensors) read their matrices from shared memory and skip this.
+    bool uses_const = false;
+    for (int sg = 0; sg < p.n_stages; sg++)
+        uses_const = uses_const || p.stage[sg].kind == 1;
+    if (uses_const) {
+        void *sym = nullptr;
+        JB_CUDA(cudaGetSymbolAddress(&sym, g_chain_const));
+        ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
+        JB_CUDA(cudaGetLastError());
+    }
+    (void)staging;
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
     auto kernel = ChainKernel<R>;
@@ -869,8 +881,10 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     }
     ChainLayout lay;
     const int wide = spec.elem_bytes == 8 ? 5 : 4;
-    if (!PlanChain(spec, max_tile_bits, wide, &lay, why) &&
-        !PlanChain(spec, max_tile_bits, wide - 1, &lay, why))
+    // small tensors are launch-latency bound: no register stages -> no constant-bank upload, one launch
+    const bool reg_stages = x0_elems > double(1 << 15);
+    if (!PlanChain(spec, max_tile_bits, wide, &lay, why, 0, reg_stages) &&
+        !PlanChain(spec, max_tile_bits, wide - 1, &lay, why, 0, reg_stages))
         return 1;
     {
         const size_t smem =

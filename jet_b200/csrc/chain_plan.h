@@ -175,7 +175,7 @@ inline bool ChainReplay(const ChainSpec &spec, std::vector<std::vector<int>> *x_
 // tile must contain (coalescing run = 2^lane_bits elements).  Fails if the tile would exceed
 // max_tile_bits.
 inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, ChainLayout *out,
-                      std::string *why, int extra_quiet = 0)
+                      std::string *why, int extra_quiet = 0, bool register_stages = true)
 {
     using namespace chain_detail;
     std::string dummy;
@@ -422,7 +422,7 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
             G.kind = 0;
             std::vector<int> occupied = sp[i].alive_after; // invariant over a run of in-place steps
             std::sort(occupied.begin(), occupied.end());
-            if (!sp[i].in_place || static_cast<int>(occupied.size()) < local_bits ||
+            if (!register_stages || !sp[i].in_place || static_cast<int>(occupied.size()) < local_bits ||
                 static_cast<int>(sp[i].k.size()) > 3) {
                 i++;
                 continue;
