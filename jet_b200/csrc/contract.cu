@@ -341,6 +341,133 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// C(M x N) = A(M x K) B(K x N) with M, N in {1, 2, 4} and a long K: the DOTU / GEMV corner of
+// MultiplyTensorData (reference include/jet/TensorHelpers.hpp:79-111; the last step of every closed
+// network is a DOTU over the whole remaining tensor).  HBM-bound: both operands are read once,
+// coalesced; partial sums are kept in double and combined in a fixed order (deterministic).
+template <typename R, int M, int N>
+__global__ void __launch_bounds__(256)
+    SmallMnKernel(const typename Cx<R>::type *__restrict__ A, const typename Cx<R>::type *__restrict__ B,
+                  double2 *__restrict__ partial, long long K)
+{
+    using C = typename Cx<R>::type;
+    double2 acc[M][N];
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+        for (int n = 0; n < N; n++)
+            acc[m][n] = double2{0.0, 0.0};
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+#pragma unroll 4
+    for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < K; k += step) {
+        C a[M], b[N];
+#pragma unroll
+        for (int m = 0; m < M; m++)
+            a[m] = A[m * K + k];
+#pragma unroll
+        for (int n = 0; n < N; n++)
+            b[n] = B[k * N + n];
+#pragma unroll
+        for (int m = 0; m < M; m++)
+#pragma unroll
+            for (int n = 0; n < N; n++) {
+                const double ar = a[m].x, ai = a[m].y, br = b[n].x, bi = b[n].y;
+                acc[m][n].x += ar * br - ai * bi;
+                acc[m][n].y += ar * bi + ai * br;
+            }
+    }
+    __shared__ double2 red[8][M * N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            double x = acc[m][n].x, y = acc[m][n].y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x += __shfl_down_sync(0xffffffffu, x, o);
+                y += __shfl_down_sync(0xffffffffu, y, o);
+            }
+            if (lane == 0)
+                red[warp][m * N + n] = double2{x, y};
+        }
+    __syncthreads();
+    if (threadIdx.x < M * N) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < 8; w++) {
+            x += red[w][threadIdx.x].x;
+            y += red[w][threadIdx.x].y;
+        }
+        partial[static_cast<long long>(blockIdx.x) * (M * N) + threadIdx.x] = double2{x, y};
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(32)
+    SmallMnFinishKernel(const double2 *__restrict__ partial, typename Cx<R>::type *__restrict__ out, int mn, int blocks)
+{
+    using C = typename Cx<R>::type;
+    if (static_cast<int>(threadIdx.x) < mn) {
+        double x = 0.0, y = 0.0;
+        for (int b = 0; b < blocks; b++) {
+            x += partial[static_cast<long long>(b) * mn + threadIdx.x].x;
+            y += partial[static_cast<long long>(b) * mn + threadIdx.x].y;
+        }
+        out[threadIdx.x] = C{static_cast<R>(x), static_cast<R>(y)};
+    }
+}
+
+bool SmallMnEligible(int64_t m, int64_t n, int64_t k)
+{
+    auto ok = [](int64_t v) { return v == 1 || v == 2 || v == 4; };
+    return ok(m) && ok(n) && k >= 4096;
+}
+
+int SmallMnBlocks(int64_t k)
+{
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((k + 1023) / 1024, NumSMs() * 8ll)));
+}
+
+size_t SmallMnWorkspaceBytes(int64_t m, int64_t n, int64_t k)
+{
+    return sizeof(double2) * static_cast<size_t>(SmallMnBlocks(k)) * m * n;
+}
+
+template <typename R, int M>
+int LaunchSmallMnN(int64_t n, int64_t k, const void *a, const void *b, void *ws, int blocks, cudaStream_t stream)
+{
+    using C = typename Cx<R>::type;
+    const C *A = static_cast<const C *>(a);
+    const C *B = static_cast<const C *>(b);
+    double2 *P = static_cast<double2 *>(ws);
+    if (n == 1)
+        SmallMnKernel<R, M, 1><<<blocks, 256, 0, stream>>>(A, B, P, k);
+    else if (n == 2)
+        SmallMnKernel<R, M, 2><<<blocks, 256, 0, stream>>>(A, B, P, k);
+    else
+        SmallMnKernel<R, M, 4><<<blocks, 256, 0, stream>>>(A, B, P, k);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+int LaunchSmallMn(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
+                  cudaStream_t stream)
+{
+    JB_REQUIRE(ws != nullptr && ws_bytes >= SmallMnWorkspaceBytes(m, n, k), "gemm: workspace too small");
+    const int blocks = SmallMnBlocks(k);
+    if (m == 1)
+        JB_TRY((LaunchSmallMnN<R, 1>(n, k, a, b, ws, blocks, stream)));
+    else if (m == 2)
+        JB_TRY((LaunchSmallMnN<R, 2>(n, k, a, b, ws, blocks, stream)));
+    else
+        JB_TRY((LaunchSmallMnN<R, 4>(n, k, a, b, ws, blocks, stream)));
+    SmallMnFinishKernel<R><<<1, 32, 0, stream>>>(static_cast<const double2 *>(ws),
+                                                static_cast<typename Cx<R>::type *>(c), static_cast<int>(m * n), blocks);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 struct GemmConfig {
     bool skinny;
     int bm, bn;
@@ -466,8 +593,10 @@ static bool TcEnabled()
 
 size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k)
 {
+    if (SmallMnEligible(m, n, k))
+        return SmallMnWorkspaceBytes(m, n, k);
     if (TcEnabled() && GemmTcEligible(dtype, m, n, k))
-        return GemmTcWorkspaceBytes(n, k);
+        return GemmTcWorkspaceBytes(m, n, k);
     const GemmConfig cfg = ChooseGemm(m, n, k);
     if (cfg.splits <= 1)
         return 0;
@@ -478,7 +607,13 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
                void *ws, size_t ws_bytes, cudaStream_t stream)
 {
     JB_REQUIRE(m >= 1 && n >= 1 && k >= 1, "gemm: dimensions must be positive");
-    if (TcEnabled() && GemmTcEligible(dtype, m, n, k) && ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(n, k))
+    if (SmallMnEligible(m, n, k) && ws != nullptr && ws_bytes >= SmallMnWorkspaceBytes(m, n, k)) {
+        if (dtype == JB_C64)
+            return LaunchSmallMn<float>(m, n, k, a, b, c, ws, ws_bytes, stream);
+        if (dtype == JB_C128)
+            return LaunchSmallMn<double>(m, n, k, a, b, c, ws, ws_bytes, stream);
+    }
+    if (TcEnabled() && GemmTcEligible(dtype, m, n, k) && ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(m, n, k))
         return LaunchGemmTc(m, n, k, a, b, c, ws, ws_bytes, stream);
     if (dtype == JB_C64)
         return LaunchGemmT<float>(m, n, k, a, b, c, ws, ws_bytes, stream);

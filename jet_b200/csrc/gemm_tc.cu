@@ -113,7 +113,9 @@ __device__ __forceinline__ void UmmaCommit(uint32_t bar)
 
 __global__ void __launch_bounds__(kTcThreads, 1)
     GemmTf32x3Kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     float *__restrict__ C, int ldc /*floats*/, int k_blocks, int tiles_n)
+                     float *__restrict__ C, int ldc /*floats*/, int k_blocks_total, int k_blocks_per_split, int tiles_n,
+                     int rows_total /*M*/, uint32_t tx_bytes /*bytes one stage's two TMA boxes deliver*/,
+                     long long split_stride /*floats between the partial results of two splits*/)
 {
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned stage buffers (SWIZZLE_128B requirement)
@@ -134,6 +136,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x / tiles_n;
     const int tile_n = blockIdx.x % tiles_n;
+    // split-K: blockIdx.y owns k-blocks [kb0, kb0 + k_blocks) and writes its own partial result
+    const int kb0 = blockIdx.y * k_blocks_per_split;
+    const int k_blocks = min(k_blocks_per_split, k_blocks_total - kb0);
+    C += static_cast<long long>(blockIdx.y) * split_stride;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kTcStages; s++) {
@@ -164,9 +170,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t phase = (kb / kTcStages) & 1;
                 MbarWait(empty_bar(s), phase ^ 1);
                 const uint32_t stage = smem_base + s * kStageBytes;
-                MbarArriveExpectTx(full_bar(s), 2 * kTileBytes);
-                TmaLoad2D(stage, &map_a, full_bar(s), kb * kTcBK, tile_m * kTcBM);
-                TmaLoad2D(stage + 2 * kTileBytes, &map_b, full_bar(s), kb * kTcBK, tile_n * kTcBN);
+                MbarArriveExpectTx(full_bar(s), tx_bytes);
+                TmaLoad2D(stage, &map_a, full_bar(s), (kb0 + kb) * kTcBK, tile_m * kTcBM);
+                TmaLoad2D(stage + 2 * kTileBytes, &map_b, full_bar(s), (kb0 + kb) * kTcBK, tile_n * kTcBN);
             }
         }
     }
@@ -272,10 +278,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             MbarArrive(tmem_empty_bar(buf));
         }
-        float *crow = C + static_cast<size_t>(tile_m * kTcBM + row) * ldc + static_cast<size_t>(tile_n) * kTcBN;
+        // ragged edges: rows >= M and columns >= 2N of the tile were computed from whatever the
+        // shared-memory tile held beyond the TMA box (each output depends only on its own row of A'
+        // and of B'^T, so they cannot contaminate valid outputs) and are simply not stored
+        const int cols_valid = min(kTcBN, ldc - tile_n * kTcBN);
+        if (tile_m * kTcBM + row < rows_total) {
+            float *crow = C + static_cast<size_t>(tile_m * kTcBM + row) * ldc + static_cast<size_t>(tile_n) * kTcBN;
 #pragma unroll
-        for (int j = 0; j < kTcBN; j += 4)
-            *reinterpret_cast<float4 *>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            for (int j = 0; j < kTcBN; j += 4)
+                if (j < cols_valid)
+                    *reinterpret_cast<float4 *>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -345,28 +358,92 @@ int MakeMap(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols_flo
 
 } // namespace
 
+namespace {
+
+// sum of the split-K partials in a fixed order (deterministic), accumulated in double
+__global__ void __launch_bounds__(256)
+    TcSplitReduceKernel(const float4 *__restrict__ partial, float4 *__restrict__ out, long long n4, int splits)
+{
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+        double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+        for (int z = 0; z < splits; z++) {
+            const float4 v = partial[static_cast<long long>(z) * n4 + i];
+            a += v.x;
+            b += v.y;
+            c += v.z;
+            d += v.w;
+        }
+        out[i] = make_float4(static_cast<float>(a), static_cast<float>(b), static_cast<float>(c), static_cast<float>(d));
+    }
+}
+
+struct TcShape {
+    long long tiles_m, tiles_n, k_blocks;
+    int splits;
+    long long k_blocks_per_split;
+};
+
+TcShape TcChoose(int64_t m, int64_t n, int64_t k)
+{
+    TcShape t;
+    t.tiles_m = (m + kTcBM - 1) / kTcBM;
+    t.tiles_n = (2 * n + kTcBN - 1) / kTcBN;
+    t.k_blocks = (2 * k) / kTcBK;
+    const long long tiles = t.tiles_m * t.tiles_n;
+    const int sms = NumSMs();
+    // few output tiles and a long K: split K so that the grid fills whole waves of CTAs (1 CTA/SM)
+    int best = 1;
+    if (tiles < sms) {
+        const long long max_splits = std::min<long long>(64, t.k_blocks / (4 * kTcChunk));
+        double best_eff = 0.0;
+        for (long long sp = 1; sp <= std::max<long long>(1, max_splits); sp++) {
+            const long long ctas = tiles * sp;
+            const double eff = double(ctas) / double(((ctas + sms - 1) / sms) * sms);
+            if (eff > best_eff + 0.04) { // prefer fewer splits unless clearly better
+                best_eff = eff;
+                best = static_cast<int>(sp);
+            }
+        }
+    }
+    long long kps = (t.k_blocks + best - 1) / best;
+    kps = ((kps + kTcChunk - 1) / kTcChunk) * kTcChunk;
+    t.splits = static_cast<int>((t.k_blocks + kps - 1) / kps);
+    t.k_blocks_per_split = kps;
+    return t;
+}
+
+} // namespace
+
 bool GemmTcEligible(int dtype, int64_t m, int64_t n, int64_t k)
 {
     if (dtype != JB_C64)
         return false;
-    if (m % kTcBM != 0 || (2 * n) % kTcBN != 0 || (2 * k) % kTcBK != 0)
-        return false;
-    if (k < 64 || m * n < 128 * 64)
+    // ragged M and N are served by TMA boxes smaller than the tile and a masked epilogue; K must be
+    // whole 128-byte swizzle atoms
+    if ((2 * k) % kTcBK != 0 || k < 64 || m < 32 || n < 16 || n % 2 != 0)
         return false;
     if (m > (1ll << 30) || n > (1ll << 29) || k > (1ll << 29))
         return false;
-    const long long tiles = (m / kTcBM) * ((2 * n) / kTcBN);
+    const long long tiles = ((m + kTcBM - 1) / kTcBM) * ((2 * n + kTcBN - 1) / kTcBN);
     return tiles < (1ll << 31) && static_cast<double>(m) * n * k >= double(1ll << 24);
 }
 
-size_t GemmTcWorkspaceBytes(int64_t n, int64_t k) { return static_cast<size_t>(16) * n * k; }
+size_t GemmTcWorkspaceBytes(int64_t m, int64_t n, int64_t k)
+{
+    const TcShape t = TcChoose(m, n, k);
+    size_t b = (static_cast<size_t>(16) * n * k + 255) & ~size_t(255); // B'^T
+    if (t.splits > 1)
+        b += static_cast<size_t>(8) * t.splits * m * n; // partial results
+    return b;
+}
 
-// C(MxN) = A(MxK) * B(KxN), complex64 row-major; ws holds B'^T (16*N*K bytes)
+// C(MxN) = A(MxK) * B(KxN), complex64 row-major; ws holds B'^T (16*N*K bytes) and the split-K partials
 int LaunchGemmTc(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
                  cudaStream_t stream)
 {
     JB_REQUIRE(GemmTcEligible(JB_C64, m, n, k), "gemm: shape not eligible for the tensor-core kernel");
-    JB_REQUIRE(ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(n, k), "gemm: tensor-core workspace too small");
+    JB_REQUIRE(ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(m, n, k), "gemm: tensor-core workspace too small");
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
@@ -377,14 +454,33 @@ int LaunchGemmTc(int64_t m, int64_t n, int64_t k, const void *a, const void *b, 
     dim3 eg(static_cast<unsigned>((n + 31) / 32), static_cast<unsigned>((k + 31) / 32));
     ExpandBKernel<<<eg, 256, 0, stream>>>(static_cast<const float2 *>(b), static_cast<float *>(ws), k, n);
     JB_CUDA(cudaGetLastError());
+    const TcShape t = TcChoose(m, n, k);
+    const uint32_t box_a = static_cast<uint32_t>(std::min<int64_t>(kTcBM, m));
+    const uint32_t box_b = static_cast<uint32_t>(std::min<int64_t>(kTcBN, 2 * n));
     CUtensorMap map_a, map_b;
-    JB_TRY(MakeMap(&map_a, a, static_cast<uint64_t>(m), static_cast<uint64_t>(2 * k), kTcBM));
-    JB_TRY(MakeMap(&map_b, ws, static_cast<uint64_t>(2 * n), static_cast<uint64_t>(2 * k), kTcBN));
-    const int tiles_n = static_cast<int>((2 * n) / kTcBN);
-    const long long tiles = (m / kTcBM) * tiles_n;
-    GemmTf32x3Kernel<<<static_cast<unsigned>(tiles), kTcThreads, kTcSmemBytes, stream>>>(
-        map_a, map_b, static_cast<float *>(c), static_cast<int>(2 * n), static_cast<int>((2 * k) / kTcBK), tiles_n);
+    JB_TRY(MakeMap(&map_a, a, static_cast<uint64_t>(m), static_cast<uint64_t>(2 * k), box_a));
+    JB_TRY(MakeMap(&map_b, ws, static_cast<uint64_t>(2 * n), static_cast<uint64_t>(2 * k), box_b));
+    const uint32_t tx_bytes = (box_a + box_b) * kTcBK * 4;
+    float *dst = static_cast<float *>(c);
+    float *partial = nullptr;
+    if (t.splits > 1) {
+        partial = reinterpret_cast<float *>(static_cast<unsigned char *>(ws) +
+                                            ((static_cast<size_t>(16) * n * k + 255) & ~size_t(255)));
+        dst = partial;
+    }
+    const long long tiles = t.tiles_m * t.tiles_n;
+    dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(t.splits), 1);
+    GemmTf32x3Kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(
+        map_a, map_b, dst, static_cast<int>(2 * n), static_cast<int>(t.k_blocks), static_cast<int>(t.k_blocks_per_split),
+        static_cast<int>(t.tiles_n), static_cast<int>(m), tx_bytes, static_cast<long long>(2) * m * n);
     JB_CUDA(cudaGetLastError());
+    if (t.splits > 1) {
+        const long long n4 = m * n / 2; // float4 = two complex64
+        const int rgrid = static_cast<int>(std::min<long long>((n4 + 255) / 256, NumSMs() * 8ll));
+        TcSplitReduceKernel<<<rgrid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(partial),
+                                                       static_cast<float4 *>(c), n4, t.splits);
+        JB_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -241,6 +241,45 @@ def test_gemm_tensor_core_shapes_vs_fp64(ops):
         assert np.max(np.abs(c[big] - ref[big]) / np.abs(ref[big])) < 1e-5, (m, n, k)
 
 
+def test_gemm_tensor_core_ragged_and_split_k(ops):
+    """Shapes the tcgen05 kernel serves with TMA boxes smaller than its 128 x 128 tile (M < 128, 2N < 128,
+    M not a multiple of 128) and with split-K (few output tiles, long K: the shapes of the last steps of
+    the m=20 paths).  Integer data makes FP32 exact, so the result must be bit-identical; random data
+    must stay within 2e-6 normwise of the complex128 product."""
+    rng = np.random.default_rng(45)
+    shapes = [(64, 512, 256), (32, 1024, 256), (2048, 32, 1024), (4096, 16, 512), (192, 96, 128), (320, 40, 96),
+              (512, 1024, 1 << 14), (256, 64, 1 << 15), (128, 128, 8192), (64, 32, 1 << 14)]
+    for m, n, k in shapes:
+        a = (rng.integers(-2, 3, (m, k)) + 1j * rng.integers(-2, 3, (m, k))).astype(np.complex64)
+        b = (rng.integers(-2, 3, (k, n)) + 1j * rng.integers(-2, 3, (k, n))).astype(np.complex64)
+        ref = (a.astype(np.complex128) @ b.astype(np.complex128)).astype(np.complex64)
+        assert np.array_equal(ops.gemm(a, b), ref), (m, n, k)
+        a = rand_c(rng, m * k, np.complex64).reshape(m, k)
+        b = rand_c(rng, k * n, np.complex64).reshape(k, n)
+        ref = a.astype(np.complex128) @ b.astype(np.complex128)
+        e = rel_err(ops.gemm(a, b), ref)
+        assert e < 2e-6, (m, n, k, e)
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_gemm_dot_and_gemv_long_k(ops, dtype):
+    """The DOTU / GEMV corner (M, N in {1, 2, 4}, long K: reference TensorHelpers.hpp:79-111 — the last
+    step of every closed network) runs on the streaming SmallMn kernel with double accumulation."""
+    rng = np.random.default_rng(46)
+    for m, n, k in [(1, 1, 1 << 22), (1, 1, 4096), (1, 4, 1 << 18), (4, 1, 1 << 18), (2, 2, 100003), (4, 4, 1 << 16),
+                    (2, 1, 5000), (1, 2, 1 << 20)]:
+        a = rand_c(rng, m * k, dtype).reshape(m, k)
+        b = rand_c(rng, k * n, dtype).reshape(k, n)
+        ref = a.astype(np.complex128) @ b.astype(np.complex128)
+        scale = np.sqrt(k)  # |sum| ~ sqrt(k): compare against the conditioning-free magnitude
+        err = np.max(np.abs(ops.gemm(a, b) - ref)) / scale
+        assert err < (1e-6 if dtype == np.complex64 else 1e-13), (m, n, k, err)
+    k = 1 << 20
+    a = (rng.integers(-2, 3, (1, k)) + 1j * rng.integers(-2, 3, (1, k))).astype(dtype)
+    b = (rng.integers(-2, 3, (k, 1)) + 1j * rng.integers(-2, 3, (k, 1))).astype(dtype)
+    assert np.array_equal(ops.gemm(a, b), (a.astype(np.complex128) @ b.astype(np.complex128)).astype(dtype))
+
+
 def test_gemm_tensor_core_exact_on_small_integers(ops):
     """Integer data: every partial product and sum is exact in FP32, so the tensor-core path must
     reproduce the integer result bit for bit (catches layout / swizzle / sign errors)."""
