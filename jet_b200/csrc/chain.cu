@@ -916,6 +916,10 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     out->log_tile = lay.params.log_tile;
     out->conflict_free = lay.conflict_free;
     out->n_stages = lay.params.n_stages;
+    out->launches = 1;
+    for (int sg = 0; sg < lay.params.n_stages; sg++)
+        if (lay.params.stage[sg].kind == 1)
+            out->launches = 2;
     out->modes_c = cur_m;
     out->extent_c = cur_e;
     out->flops = flops;

@@ -74,6 +74,8 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
                void *ws, size_t ws_bytes, cudaStream_t stream);
 
 // tensor-core (tcgen05, 3xTF32) complex64 GEMM for large aligned shapes (gemm_tc.cu)
+bool GemmDmmaEligible(int dtype, int64_t m, int64_t n, int64_t k); // complex128, FP64 tensor pipe (gemm_dmma.cu)
+int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, cudaStream_t stream);
 bool GemmTcEligible(int dtype, int64_t m, int64_t n, int64_t k);
 size_t GemmTcWorkspaceBytes(int64_t m, int64_t n, int64_t k);
 int LaunchGemmTc(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws,
@@ -128,6 +130,7 @@ struct ChainOp {
     int log_tile = 0;
     int conflict_free = 1;
     int n_stages = 0;
+    int launches = 1; // chain kernel, plus the matrix gather when a register stage reads the constant bank
     std::vector<unsigned char> blob; // ChainParams (chain_plan.h)
     std::vector<int32_t> modes_c;
     std::vector<int64_t> extent_c;

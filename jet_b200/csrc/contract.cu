@@ -591,10 +591,21 @@ static bool TcEnabled()
     return enabled;
 }
 
+static bool DmmaEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_DISABLE_DMMA");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
+}
+
 size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k)
 {
     if (SmallMnEligible(m, n, k))
         return SmallMnWorkspaceBytes(m, n, k);
+    if (DmmaEnabled() && GemmDmmaEligible(dtype, m, n, k))
+        return 0;
     if (TcEnabled() && GemmTcEligible(dtype, m, n, k))
         return GemmTcWorkspaceBytes(m, n, k);
     const GemmConfig cfg = ChooseGemm(m, n, k);
@@ -615,6 +626,8 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
     }
     if (TcEnabled() && GemmTcEligible(dtype, m, n, k) && ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(m, n, k))
         return LaunchGemmTc(m, n, k, a, b, c, ws, ws_bytes, stream);
+    if (DmmaEnabled() && GemmDmmaEligible(dtype, m, n, k))
+        return LaunchGemmDmma(m, n, k, a, b, c, stream);
     if (dtype == JB_C64)
         return LaunchGemmT<float>(m, n, k, a, b, c, ws, ws_bytes, stream);
     if (dtype == JB_C128)
@@ -750,7 +763,11 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
     const int64_t size_a = P.m * P.k, size_b = P.k * P.n;
 
     // ---- stream kernel: one operand small, all extents powers of two ----------------------------
-    if (pow2 && std::min(size_a, size_b) <= kStreamMaxResident) {
+    // complex128 steps whose resident operand is a 32 x 32 or larger matrix are bound by the FP64 pipe,
+    // not by HBM (>= 8 flop/B): they go to TTGT + the DMMA GEMM instead of the FP64-FMA stream kernel
+    const bool dmma_step = dtype == JB_C128 && P.k >= 32 && P.n >= 32 && size_a >= size_b &&
+                           GemmDmmaEligible(dtype, P.m, P.n, P.k) && DmmaEnabled();
+    if (pow2 && std::min(size_a, size_b) <= kStreamMaxResident && !dmma_step) {
         const bool stream_a = size_a >= size_b; // A streamed, B resident
         const int rs = stream_a ? rank_a : rank_b;
         const int rr = stream_a ? rank_b : rank_a;

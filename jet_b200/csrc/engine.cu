@@ -688,7 +688,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         if (op.kernel == 2) {
             S.chains++;
             S.steps_chained += static_cast<int32_t>(op.steps.size());
-            S.launches_per_slice += 2; // matrix gather + chain kernel (plus one D2D copy node)
+            S.launches_per_slice += op.chain.launches; // chain kernel (+ matrix gather)
             S.fused_bytes_per_slice += op.chain.bytes;
         }
         else {
@@ -911,7 +911,7 @@ int jb_plan_ops(const jb_plan *p, jb_op_info_t *ops, int32_t cap, int32_t *count
         o.pad = 0;
         o.flops = o.bytes = o.step_bytes = 0.0;
         if (op.kernel == 2) {
-            o.launches = 2;
+            o.launches = op.chain.launches;
             o.flops = op.chain.flops;
             o.bytes = op.chain.bytes;
             o.step_bytes = op.chain.step_bytes;

@@ -280,6 +280,38 @@ def test_gemm_dot_and_gemv_long_k(ops, dtype):
     assert np.array_equal(ops.gemm(a, b), (a.astype(np.complex128) @ b.astype(np.complex128)).astype(dtype))
 
 
+def test_gemm_fp64_tensor_pipe_shapes(ops):
+    """complex128 shapes served by the DMMA kernel (gemm_dmma.cu: K % 8 == 0, M >= 32, N >= 16, ragged
+    M / N tiles): 1e-12 normwise against numpy's complex128 product (BASELINE tolerance), and
+    bit-identical on small integers (FP64 exact)."""
+    rng = np.random.default_rng(48)
+    for m, n, k in [(128, 64, 64), (4096, 64, 64), (1 << 15, 64, 64), (200, 48, 24), (32, 16, 8), (1000, 100, 200),
+                    (512, 512, 512), (96, 200, 1024)]:
+        a = rand_c(rng, m * k, np.complex128).reshape(m, k)
+        b = rand_c(rng, k * n, np.complex128).reshape(k, n)
+        ref = a @ b
+        e = rel_err(ops.gemm(a, b), ref)
+        assert e < 1e-12, (m, n, k, e)
+        a = (rng.integers(-3, 4, (m, k)) + 1j * rng.integers(-3, 4, (m, k))).astype(np.complex128)
+        b = (rng.integers(-3, 4, (k, n)) + 1j * rng.integers(-3, 4, (k, n))).astype(np.complex128)
+        assert np.array_equal(ops.gemm(a, b), a @ b), (m, n, k)
+
+
+def test_contract_c128_compute_bound_step_uses_ttgt_dmma(ops):
+    """The GBS fock-8 step shape (dim-8 indices: M large, N = K = 64) in complex128 is routed to
+    TTGT + DMMA (kernel 1) and matches the oracle's ContractTensors to 1e-12."""
+    rng = np.random.default_rng(49)
+    shape_a, ia = [8, 8, 8, 8, 8], [0, 1, 2, 3, 4]
+    shape_b, ib = [8, 8, 8, 8], [3, 100, 1, 101]
+    a = rand_c(rng, 8 ** 5, np.complex128).reshape(shape_a)
+    b = rand_c(rng, 8 ** 4, np.complex128).reshape(shape_b)
+    info = ops.contract_info(np.complex128, shape_a, ia, shape_b, ib)
+    assert info.kernel == 1 and info.m == 512 and info.n == 64 and info.k == 64
+    out, modes = ops.contract(a, ia, b, ib)
+    _, ref = jo.contract(([str(i) for i in ia], a), ([str(i) for i in ib], b))
+    assert rel_err(out, ref) < 1e-12
+
+
 def test_gemm_tensor_core_exact_on_small_integers(ops):
     """Integer data: every partial product and sum is exact in FP32, so the tensor-core path must
     reproduce the integer result bit for bit (catches layout / swizzle / sign errors)."""
