@@ -75,7 +75,9 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
 
 // tensor-core (tcgen05, 3xTF32) complex64 GEMM for large aligned shapes (gemm_tc.cu)
 bool GemmDmmaEligible(int dtype, int64_t m, int64_t n, int64_t k); // complex128, FP64 tensor pipe (gemm_dmma.cu)
-int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, cudaStream_t stream);
+size_t GemmDmmaWorkspaceBytes(int64_t m, int64_t n, int64_t k);
+int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
+                   cudaStream_t stream);
 bool GemmTcEligible(int dtype, int64_t m, int64_t n, int64_t k);
 size_t GemmTcWorkspaceBytes(int64_t m, int64_t n, int64_t k);
 int LaunchGemmTc(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws,

@@ -605,7 +605,7 @@ size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k)
     if (SmallMnEligible(m, n, k))
         return SmallMnWorkspaceBytes(m, n, k);
     if (DmmaEnabled() && GemmDmmaEligible(dtype, m, n, k))
-        return 0;
+        return GemmDmmaWorkspaceBytes(m, n, k);
     if (TcEnabled() && GemmTcEligible(dtype, m, n, k))
         return GemmTcWorkspaceBytes(m, n, k);
     const GemmConfig cfg = ChooseGemm(m, n, k);
@@ -626,8 +626,9 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
     }
     if (TcEnabled() && GemmTcEligible(dtype, m, n, k) && ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(m, n, k))
         return LaunchGemmTc(m, n, k, a, b, c, ws, ws_bytes, stream);
-    if (DmmaEnabled() && GemmDmmaEligible(dtype, m, n, k))
-        return LaunchGemmDmma(m, n, k, a, b, c, stream);
+    if (DmmaEnabled() && GemmDmmaEligible(dtype, m, n, k) &&
+        (GemmDmmaWorkspaceBytes(m, n, k) == 0 || (ws != nullptr && ws_bytes >= GemmDmmaWorkspaceBytes(m, n, k))))
+        return LaunchGemmDmma(m, n, k, a, b, c, ws, ws_bytes, stream);
     if (dtype == JB_C64)
         return LaunchGemmT<float>(m, n, k, a, b, c, ws, ws_bytes, stream);
     if (dtype == JB_C128)

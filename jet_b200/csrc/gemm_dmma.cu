@@ -50,7 +50,7 @@ __device__ __forceinline__ void CpAsync16(unsigned dst, const void *src, bool va
 
 __global__ void __launch_bounds__(kDmThreads, 1)
     GemmDmmaKernel(const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C,
-                   long long M, long long N, long long K, int tiles_n)
+                   long long M, long long N, long long K, int tiles_n, int k_tiles_per_split)
 {
     extern __shared__ __align__(16) double dm_smem[];
     double *As = dm_smem;
@@ -59,12 +59,16 @@ __global__ void __launch_bounds__(kDmThreads, 1)
     const int wm = warp >> 1, wn = warp & 1;
     const long long m0 = static_cast<long long>(blockIdx.x / tiles_n) * kDmBM;
     const long long n0 = static_cast<long long>(blockIdx.x % tiles_n) * kDmBN;
-    const int k_tiles = static_cast<int>(K / kDmBK);
+    // split-K: blockIdx.y owns k-tiles [kt0, kt0 + k_tiles) and writes its own partial result
+    const int k_tiles_total = static_cast<int>(K / kDmBK);
+    const int kt0 = blockIdx.y * k_tiles_per_split;
+    const int k_tiles = min(k_tiles_per_split, k_tiles_total - kt0);
+    C += static_cast<long long>(blockIdx.y) * M * N;
     const unsigned as_s = static_cast<unsigned>(__cvta_generic_to_shared(As));
     const unsigned bs_s = static_cast<unsigned>(__cvta_generic_to_shared(Bs));
 
     auto load_stage = [&](int kt, int s) {
-        const long long k0 = static_cast<long long>(kt) * kDmBK;
+        const long long k0 = static_cast<long long>(kt0 + kt) * kDmBK;
 #pragma unroll
         for (int i = 0; i < (kDmBM * kDmBK) / kDmThreads; i++) { // A: 1024 complex, 4 per thread
             const int q = i * kDmThreads + tid;
@@ -151,20 +155,66 @@ __global__ void __launch_bounds__(kDmThreads, 1)
 
 } // namespace
 
+namespace {
+
+// sum of the split-K partials in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+    DmmaSplitReduceKernel(const double2 *__restrict__ partial, double2 *__restrict__ out, long long mn, int splits)
+{
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < mn; i += step) {
+        double re = 0.0, im = 0.0;
+        for (int z = 0; z < splits; z++) {
+            const double2 v = partial[static_cast<long long>(z) * mn + i];
+            re += v.x;
+            im += v.y;
+        }
+        out[i] = double2{re, im};
+    }
+}
+
+struct DmmaShape {
+    long long tiles;
+    int tiles_n, splits, k_tiles_per_split;
+};
+
+DmmaShape DmmaChoose(int64_t m, int64_t n, int64_t k)
+{
+    DmmaShape t;
+    t.tiles_n = static_cast<int>((n + kDmBN - 1) / kDmBN);
+    t.tiles = ((m + kDmBM - 1) / kDmBM) * t.tiles_n;
+    const long long k_tiles = k / kDmBK;
+    const int sms = NumSMs();
+    long long splits = 1;
+    if (t.tiles < sms && k_tiles >= 64) // few output tiles and a long K: fill the machine along K
+        splits = std::min<long long>({(2ll * sms + t.tiles - 1) / t.tiles, k_tiles / 16, 1024ll});
+    splits = std::max<long long>(splits, 1);
+    const long long per = (k_tiles + splits - 1) / splits;
+    t.k_tiles_per_split = static_cast<int>(per);
+    t.splits = static_cast<int>((k_tiles + per - 1) / per);
+    return t;
+}
+
+} // namespace
+
 bool GemmDmmaEligible(int dtype, int64_t m, int64_t n, int64_t k)
 {
     if (dtype != JB_C128 || k % kDmBK != 0 || k < kDmBK || m < 32 || n < 16)
         return false;
     const long long tiles = ((m + kDmBM - 1) / kDmBM) * ((n + kDmBN - 1) / kDmBN);
-    if (tiles >= (1ll << 31))
-        return false;
-    // few output tiles with a long K are better served by the split-K FMA kernel
-    if (tiles < NumSMs() / 2 && k >= 4096)
+    if (tiles >= (1ll << 31) || k / kDmBK >= (1ll << 31))
         return false;
     return static_cast<double>(m) * n * k >= double(1 << 18);
 }
 
-int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, cudaStream_t stream)
+size_t GemmDmmaWorkspaceBytes(int64_t m, int64_t n, int64_t k)
+{
+    const DmmaShape t = DmmaChoose(m, n, k);
+    return t.splits > 1 ? sizeof(double2) * static_cast<size_t>(t.splits) * m * n : 0;
+}
+
+int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
+                   cudaStream_t stream)
 {
     JB_REQUIRE(GemmDmmaEligible(JB_C128, m, n, k), "gemm: shape not eligible for the FP64 tensor-core kernel");
     static std::once_flag attr_once;
@@ -174,11 +224,24 @@ int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b
                                         static_cast<int>(kDmSmemBytes));
     });
     JB_CUDA(attr_err);
-    const int tiles_n = static_cast<int>((n + kDmBN - 1) / kDmBN);
-    const long long tiles = ((m + kDmBM - 1) / kDmBM) * tiles_n;
-    GemmDmmaKernel<<<static_cast<unsigned>(tiles), kDmThreads, kDmSmemBytes, stream>>>(
-        static_cast<const double2 *>(a), static_cast<const double2 *>(b), static_cast<double2 *>(c), m, n, k, tiles_n);
+    const DmmaShape t = DmmaChoose(m, n, k);
+    double2 *dst = static_cast<double2 *>(c);
+    if (t.splits > 1) {
+        JB_REQUIRE(ws != nullptr && ws_bytes >= GemmDmmaWorkspaceBytes(m, n, k), "gemm: split-K workspace too small");
+        dst = static_cast<double2 *>(ws);
+    }
+    dim3 grid(static_cast<unsigned>(t.tiles), static_cast<unsigned>(t.splits), 1);
+    GemmDmmaKernel<<<grid, kDmThreads, kDmSmemBytes, stream>>>(static_cast<const double2 *>(a),
+                                                               static_cast<const double2 *>(b), dst, m, n, k, t.tiles_n,
+                                                               t.k_tiles_per_split);
     JB_CUDA(cudaGetLastError());
+    if (t.splits > 1) {
+        const long long mn = m * n;
+        const int rgrid = static_cast<int>(std::min<long long>((mn + 255) / 256, NumSMs() * 8ll));
+        DmmaSplitReduceKernel<<<rgrid, 256, 0, stream>>>(static_cast<const double2 *>(ws), static_cast<double2 *>(c), mn,
+                                                        t.splits);
+        JB_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

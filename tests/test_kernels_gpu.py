@@ -286,7 +286,7 @@ def test_gemm_fp64_tensor_pipe_shapes(ops):
     bit-identical on small integers (FP64 exact)."""
     rng = np.random.default_rng(48)
     for m, n, k in [(128, 64, 64), (4096, 64, 64), (1 << 15, 64, 64), (200, 48, 24), (32, 16, 8), (1000, 100, 200),
-                    (512, 512, 512), (96, 200, 1024)]:
+                    (512, 512, 512), (96, 200, 1024), (64, 64, 1 << 16), (128, 32, 40000)]:
         a = rand_c(rng, m * k, np.complex128).reshape(m, k)
         b = rand_c(rng, k * n, np.complex128).reshape(k, n)
         ref = a @ b
