@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libjetref.so")
-DATA_DIR = os.path.join(HERE, "_ref", "data_files")
+DATA_DIR = os.path.join(os.path.dirname(HERE), "data", "_ref")
 
 _lib = None
 

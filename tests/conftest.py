@@ -12,12 +12,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-DATA_DIR = os.path.join(ROOT, "oracle", "_ref", "data_files")
+DATA_DIR = os.path.join(ROOT, "data", "_ref")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
 @pytest.fixture(scope="session")
 def data_dir():
     if not os.path.isdir(DATA_DIR):
-        pytest.skip("oracle/_ref/data_files missing (run `make -C oracle` where /root/reference exists)")
+        pytest.skip("data/_ref missing (run `make -C oracle` where /root/reference exists)")
     return DATA_DIR

@@ -22,7 +22,7 @@ from jet_b200.distributed import slice_range, reduce_amplitude
 from oracle import jet_oracle as jo
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-net = jo.Network.from_file(os.path.join({root!r}, "oracle", "_ref", "data_files", "m10.json"), "complex64")
+net = jo.Network.from_file(os.path.join({root!r}, "data", "_ref", "m10.json"), "complex64")
 sliced = "p7 s7 h4 m1 m2 I2".split()
 first, count = slice_range(6, world, rank)          # 6 of the 64 slices -> uneven split at world=4
 part = jo.amplitude(net, sliced, range(first, first + count))

@@ -21,7 +21,7 @@ local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-net = NetworkFile.load(os.path.join({root!r}, "oracle", "_ref", "data_files", "m10.json"), np.complex64)
+net = NetworkFile.load(os.path.join({root!r}, "data", "_ref", "m10.json"), np.complex64)
 plan = ContractionPlan(net, "p7 s7 h4 m1 m2 I2".split(), device=local)
 first, count = slice_range(plan.num_slices, world, rank)
 plan.reset(); plan.run(first, count)

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from jet_b200 import ContractionPlan, NetworkFile, ops  # noqa: E402
 
-DATA = os.path.join(ROOT, "oracle", "_ref", "data_files")
+DATA = os.path.join(ROOT, "data", "_ref")
 dev = torch.device("cuda:0")
 
 

@@ -15,7 +15,7 @@ dimension 2 — the structure the tags of the reference's m10.json show (`FSIM` 
 with the single-qubit gates, inputs and outputs absorbed into them.
 
   python tools/sycamore_gen.py --rows 9 --cols 6 --remove 0,0 --cycles 20 --seed 1 --target-log2 28 \
-         --out oracle/_ref/data_files/syc53_m20.json
+         --out data/syc53_m20.json
 writes the network + path JSON and <out>.meta.json (sliced indices, costs).
 `amplitude_statevector` is an independent brute-force check used by the tests on small lattices.
 """
@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--trials", type=int, default=8)
     ap.add_argument("--target-log2", type=int, default=28)
-    ap.add_argument("--out", default=os.path.join(ROOT, "oracle", "_ref", "data_files", "syc53_m20.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "data", "syc53_m20.json"))
     args = ap.parse_args()
     removed = tuple(int(v) for v in args.remove.split(",")) if args.remove else None
     _, _, _, leaves, path, meta = build(args.rows, args.cols, removed, args.cycles, args.seed, args.trials, args.target_log2)
