@@ -5,9 +5,10 @@ Layers:
   _lib.py        ctypes loader (fails loudly if the library is missing; no CPU fallback)
   ops.py         operator layer: permute / contract / gemm / add / slice_index
   plan.py        NetworkFile (reference JSON format) + ContractionPlan (whole sliced network on a GPU)
+                 + LanePlans (several slices in flight on one GPU)
 """
 from ._lib import JetB200Error  # noqa: F401
-from .plan import ContractionPlan, NetworkFile  # noqa: F401
+from .plan import ContractionPlan, LanePlans, NetworkFile  # noqa: F401
 from . import ops  # noqa: F401
 
 __version__ = "0.1.0"

@@ -214,8 +214,8 @@ template <> struct StageB<double> {
 // per-lane register file.  Measured (tools/micro/ffma2_mix.cu): 97 % of the FMA pipe with two warps
 // per scheduler, against 53 % when the same entries come from shared memory.
 // One 16 KB region per slot; a plan (or the operator-level entry point) owns a slot while it lives.
-constexpr int kChainConstSlots = 3;
-constexpr int kChainConstEntries = 1024; // 16-byte entries per slot
+constexpr int kChainConstSlots = 6;      // 5 plans per device (LanePlans) + the operator-level slot
+constexpr int kChainConstEntries = 512;  // 16-byte entries per slot (8 KB; 48 KB of the 64 KB bank in all)
 __constant__ uint4 g_chain_const[kChainConstSlots * kChainConstEntries];
 
 template <typename R> __device__ __forceinline__ typename StageB<R>::type ConstB(int idx);
@@ -716,7 +716,6 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
 {
     using C = typename Cplx<R>::type;
     JB_REQUIRE(slot >= 0 && slot < kChainConstSlots && staging != nullptr, "chain: no constant-bank slot");
-    JB_REQUIRE(p.resident_elems <= kChainConstEntries, "chain: too many matrix entries");
     p.const_base = slot * kChainConstEntries;
     // The matrices of the register stages go straight into this launch's constant-bank slot: the
     // bank is ordinary device memory behind the symbol's address, and a kernel boundary separates
@@ -726,6 +725,7 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     for (int sg = 0; sg < p.n_stages; sg++)
         uses_const = uses_const || p.stage[sg].kind == 1;
     if (uses_const) {
+        JB_REQUIRE(p.resident_elems <= kChainConstEntries, "chain: too many matrix entries");
         void *sym = nullptr;
         JB_CUDA(cudaGetSymbolAddress(&sym, g_chain_const));
         ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
@@ -882,10 +882,17 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     ChainLayout lay;
     const int wide = spec.elem_bytes == 8 ? 5 : 4;
     // small tensors are launch-latency bound: no register stages -> no constant-bank upload, one launch
-    const bool reg_stages = x0_elems > double(1 << 15);
+    bool reg_stages = x0_elems > double(1 << 15);
     if (!PlanChain(spec, max_tile_bits, wide, &lay, why, 0, reg_stages) &&
         !PlanChain(spec, max_tile_bits, wide - 1, &lay, why, 0, reg_stages))
         return 1;
+    if (reg_stages && lay.params.resident_elems > kChainConstEntries) {
+        // the matrices do not fit a constant-bank slot: all steps through the shared-memory path
+        reg_stages = false;
+        if (!PlanChain(spec, max_tile_bits, wide, &lay, why, 0, false) &&
+            !PlanChain(spec, max_tile_bits, wide - 1, &lay, why, 0, false))
+            return 1;
+    }
     {
         const size_t smem =
             spec.elem_bytes == 8
@@ -895,7 +902,7 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
             *why = "shared memory";
             return 1;
         }
-        if (lay.params.resident_elems > kChainConstEntries) {
+        if (reg_stages && lay.params.resident_elems > kChainConstEntries) {
             *why = "too many matrix entries";
             return 1;
         }

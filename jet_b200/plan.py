@@ -235,3 +235,71 @@ class ContractionPlan:
         else:
             self.run_list(list(slice_ids))
         return self.result()
+
+
+class LanePlans:
+    """K ContractionPlans of the same sliced network on one GPU — each with its own arena, stream and
+    CUDA graph — so that K independent slice contractions are in flight at once: slice number j of a
+    run goes to lane j % K.  The reference runs the tasks of different slices concurrently on Taskflow
+    worker threads (include/jet/TaskBasedContractor.hpp:322, examples/paper_benchmarks/CPU/
+    jet_cpu_m10/jet_sliced.cpp:69-93); this is the same idea with streams.  It pays off when one slice
+    is too small to fill the GPU (m10, GBS fock4: every kernel is a handful of CTAs and the slice is
+    launch-latency bound); large slices (m12, m=20) gain nothing and should use one lane.
+    The result is the sum of the lanes' FP64 accumulators in lane order: deterministic for a given K."""
+
+    MAX_LANES = 5  # constant-bank slots available to plans (jet_b200/csrc/chain.cu)
+
+    def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), lanes: int = 2, device: int = 0, **kw):
+        if not 1 <= lanes <= self.MAX_LANES:
+            raise ValueError(f"lanes must be in 1..{self.MAX_LANES}")
+        self.plans = [ContractionPlan(net, sliced, device=device, **kw) for _ in range(lanes)]
+        p0 = self.plans[0]
+        self.num_slices, self.result_elems, self.result_shape = p0.num_slices, p0.result_elems, p0.result_shape
+        self.result_indices, self.stats, self.dtype = p0.result_indices, p0.stats, p0.dtype
+
+    def close(self):
+        for p in self.plans:
+            p.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def streams(self) -> List[int]:
+        return [p.stream() for p in self.plans]
+
+    def upload_ptrs(self, ptrs: Sequence[int]):
+        for p in self.plans:
+            p.upload_ptrs(ptrs)
+
+    def reset(self):
+        for p in self.plans:
+            p.reset()
+
+    def run_list(self, ids: Sequence[int]):
+        k = len(self.plans)
+        for lane, p in enumerate(self.plans):
+            mine = list(ids[lane::k])
+            if mine:
+                p.run_list(mine)
+
+    def run(self, first: int = 0, count: Optional[int] = None):
+        count = self.num_slices - first if count is None else count
+        self.run_list(range(first, first + count))
+
+    def sync(self):
+        for p in self.plans:
+            p.sync()
+
+    def result(self) -> np.ndarray:
+        out = self.plans[0].result()
+        for p in self.plans[1:]:
+            out = out + p.result()
+        return out
+
+    def amplitude(self, slice_ids: Optional[Sequence[int]] = None) -> np.ndarray:
+        self.reset()
+        self.run_list(list(range(self.num_slices)) if slice_ids is None else list(slice_ids))
+        return self.result()
