@@ -9,19 +9,27 @@
 //        B'[2k][2n] = Re B, B'[2k][2n+1] = Im B, B'[2k+1][2n] = -Im B, B'[2k+1][2n+1] = Re B.
 //    A and C need no conversion at all; B' is built (transposed, K-major) by a small pre-pass.
 //    8*M*N*K real flops, exactly the complex product.
-//  * 3xTF32: every fp32 operand tile is split IN SHARED MEMORY into hi = fp32 with the low 13
-//    mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32); the
-//    accumulator receives lo*hi + hi*lo + hi*hi (the lo*lo term, ~2^-22 relative, is dropped).
-//    FP32 accumulation in TMEM.  Global memory is read once: TMA brings the raw fp32 tile, four
-//    "splitter" warps rewrite it as hi in place and produce the lo tile beside it.
+//  * 3xTF32: every fp32 operand is split into hi = fp32 with the low 13 mantissa bits cleared
+//    (exactly representable in TF32) and lo = x - hi (exact in fp32); the accumulator receives
+//    lo*hi + hi*lo + hi*hi (the lo*lo term, ~2^-22 relative, is dropped).  FP32 accumulation in TMEM.
+//    Two variants of where the split happens (template parameter PRE):
+//      PRE = true  (both M and N >= 1024): a pre-pass in global memory (A: SplitHiLoKernel, B: inside
+//        the B' expansion); TMA brings four tiles per stage.  The kernel is bound by shared-memory
+//        bandwidth (three MMAs read both operand tiles from shared memory per K step) and splitting
+//        inside shared memory adds a read and two writes of every tile to that same bottleneck
+//        (measured 180 -> 225 TFLOP/s on 2^13 x 2^14 x 2^12).
+//      PRE = false (skinny or K-heavy shapes, where operand preparation is not negligible against
+//        the GEMM): TMA brings the raw fp32 tiles, four "splitter" warps rewrite each as hi in place
+//        and produce the lo tile beside it; global memory is read once.
 //  * The tensor core adds into its FP32 accumulator with truncation, so a long K loop in TMEM
 //    drifts (measured 1e-5 relative at K = 1024).  The accumulation is therefore chunked: every
 //    kTcChunk k-blocks the TMEM partial sum is promoted (tcgen05.ld) into FP32 registers with
 //    round-to-nearest adds, double-buffered in TMEM so the next chunk's MMAs overlap the drain.
-//  * Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single
-//    thread tcgen05.mma issuer, warps 2-5 = splitters, warps 6-9 = register accumulators +
-//    epilogue.  mbarriers: full (TMA landed) -> split (hi/lo ready) -> empty (tcgen05.commit: the
-//    MMAs reading the stage retired); tmem_full / tmem_empty per accumulator buffer.
+//  * Warp roles per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + single thread
+//    tcgen05.mma issuer, then (PRE = false only) 4 splitter warps, then 4 register-accumulator +
+//    epilogue warps: 192 / 320 threads.  mbarriers: full (TMA landed) [-> split (hi/lo ready)] ->
+//    empty (tcgen05.commit: the MMAs reading the stage retired); tmem_full / tmem_empty per
+//    accumulator buffer.
 //  * Tile 128 x 128 (real columns) x 32 (one 128-byte swizzle atom of K per stage), UMMA
 //    M128 N128 K8 kind::tf32, operands K-major with the 128B swizzle TMA writes.
 #include <cuda.h>
@@ -38,8 +46,9 @@ constexpr int kTcBM = 128;        // rows of C' per CTA
 constexpr int kTcBN = 128;        // real columns of C' per CTA (64 complex)
 constexpr int kTcBK = 32;         // floats of K' per stage (128 bytes)
 constexpr int kTcStages = 3;
-constexpr int kTcThreads = 320;   // TMA warp, MMA warp, 4 splitter warps, 4 accumulator warps
+template <bool PRE> constexpr int TcThreads() { return PRE ? 192 : 320; } // TMA, MMA, [4 splitters,] 4 accumulators
 constexpr int kTcChunk = 4;       // k-blocks accumulated in TMEM before promotion to registers
+constexpr int kTcBand = 16;       // tile rows per rasterisation band
 constexpr uint32_t kTileBytes = kTcBM * kTcBK * 4; // 16 KB (A and B tiles have the same size)
 constexpr uint32_t kStageBytes = 4 * kTileBytes;   // A_hi, A_lo, B_hi, B_lo
 constexpr uint32_t kTcSmemBytes = kTcStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -111,8 +120,10 @@ __device__ __forceinline__ void UmmaCommit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
-    GemmTf32x3Kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+template <bool PRE>
+__global__ void __launch_bounds__(TcThreads<PRE>(), 1)
+    GemmTf32x3Kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_lo,
                      float *__restrict__ C, int ldc /*floats*/, int k_blocks_total, int k_blocks_per_split, int tiles_n,
                      int rows_total /*M*/, uint32_t tx_bytes /*bytes one stage's two TMA boxes deliver*/,
                      long long split_stride /*floats between the partial results of two splits*/)
@@ -122,7 +133,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t smem_base = (SmemAddr(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_gen = smem_raw + (smem_base - SmemAddr(smem_raw));
     const uint32_t bars = smem_base + kTcStages * kStageBytes;
-    // barrier layout (8 bytes each): full[3], split[3], empty[3], tmem_full, then the TMEM address
+    // barrier layout (8 bytes each): full[3], split[3], empty[3], tmem_full[2], tmem_empty[2], then the TMEM address
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto split_bar = [&](int s) { return bars + 8u * (kTcStages + s); };
     auto empty_bar = [&](int s) { return bars + 8u * (2 * kTcStages + s); };
@@ -134,8 +145,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x / tiles_n;
-    const int tile_n = blockIdx.x % tiles_n;
+    // Rasterisation: CTAs that run at the same time should share operand tiles in L2.  Row-major
+    // order over (tile_m, tile_n) makes one wave of 148 CTAs read 1 A tile and 148 different B tiles
+    // (B is then re-read from DRAM once per tile row: 64 x 2 GB on the m=20 shapes).  Bands of
+    // kTcBand tile rows, tile_m fastest inside a band: a wave covers ~16 x 9 tiles.
+    const int tiles_m = (rows_total + kTcBM - 1) / kTcBM;
+    const int band = blockIdx.x / (kTcBand * tiles_n);
+    const int first_m = band * kTcBand;
+    const int band_rows = min(kTcBand, tiles_m - first_m);
+    const int in_band = blockIdx.x - band * (kTcBand * tiles_n);
+    const int tile_m = first_m + in_band % band_rows;
+    const int tile_n = in_band / band_rows;
     // split-K: blockIdx.y owns k-blocks [kb0, kb0 + k_blocks) and writes its own partial result
     const int kb0 = blockIdx.y * k_blocks_per_split;
     const int k_blocks = min(k_blocks_per_split, k_blocks_total - kb0);
@@ -173,6 +193,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 MbarArriveExpectTx(full_bar(s), tx_bytes);
                 TmaLoad2D(stage, &map_a, full_bar(s), (kb0 + kb) * kTcBK, tile_m * kTcBM);
                 TmaLoad2D(stage + 2 * kTileBytes, &map_b, full_bar(s), (kb0 + kb) * kTcBK, tile_n * kTcBN);
+                if constexpr (PRE) {
+                    TmaLoad2D(stage + kTileBytes, &map_a_lo, full_bar(s), (kb0 + kb) * kTcBK, tile_m * kTcBM);
+                    TmaLoad2D(stage + 3 * kTileBytes, &map_b_lo, full_bar(s), (kb0 + kb) * kTcBK, tile_n * kTcBN);
+                }
             }
         }
     }
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const bool chunk_last = (kb % kTcChunk) == kTcChunk - 1 || kb == k_blocks - 1;
             if (chunk_first) // the accumulator warps have drained this TMEM buffer
                 MbarWait(tmem_empty_bar(buf), ((chunk >> 1) & 1) ^ 1);
-            MbarWait(split_bar(s), phase);
+            MbarWait(PRE ? full_bar(s) : split_bar(s), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t stage = smem_base + s * kStageBytes;
@@ -210,8 +234,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             __syncwarp();
         }
     }
-    else if (warp < 6) {
-        // ===== splitters (128 threads) =====
+    else if (!PRE && warp < 6) {
+        // ===== splitters (128 threads, PRE = false) =====
         const int t = threadIdx.x - 64;
         for (int kb = 0; kb < k_blocks; kb++) {
             const int s = kb % kTcStages;
@@ -298,10 +322,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
 }
 
-// B (K x N complex, row-major) -> B'^T (2N x 2K floats, K-major):
+__device__ __forceinline__ float TfHi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// B (K x N complex, row-major) -> B'^T (2N x 2K floats, K-major), split into hi and lo:
 //   row 2n   = (Re B[k][n], -Im B[k][n]) over k;  row 2n+1 = (Im B[k][n], Re B[k][n]) over k
+template <bool PRE>
 __global__ void __launch_bounds__(256)
-    ExpandBKernel(const float2 *__restrict__ B, float *__restrict__ Bt, long long K, long long N)
+    ExpandBKernel(const float2 *__restrict__ B, float *__restrict__ Bt_hi, float *__restrict__ Bt_lo, long long K,
+                  long long N)
 {
     __shared__ float2 tile[32][33];
     const long long k0 = static_cast<long long>(blockIdx.y) * 32, n0 = static_cast<long long>(blockIdx.x) * 32;
@@ -315,11 +343,33 @@ __global__ void __launch_bounds__(256)
         const long long n = n0 + r, k = k0 + tx;
         if (n < N && k < K) {
             const float2 v = tile[tx][r];
-            float2 *row0 = reinterpret_cast<float2 *>(Bt + (2 * n) * (2 * K)) + k;
-            float2 *row1 = reinterpret_cast<float2 *>(Bt + (2 * n + 1) * (2 * K)) + k;
-            *row0 = float2{v.x, -v.y};
-            *row1 = float2{v.y, v.x};
+            const long long o0 = (2 * n) * (2 * K) + 2 * k, o1 = (2 * n + 1) * (2 * K) + 2 * k;
+            if constexpr (PRE) {
+                const float hx = TfHi(v.x), hy = TfHi(v.y);
+                const float lx = v.x - hx, ly = v.y - hy;
+                *reinterpret_cast<float2 *>(Bt_hi + o0) = float2{hx, -hy};
+                *reinterpret_cast<float2 *>(Bt_hi + o1) = float2{hy, hx};
+                *reinterpret_cast<float2 *>(Bt_lo + o0) = float2{lx, -ly};
+                *reinterpret_cast<float2 *>(Bt_lo + o1) = float2{ly, lx};
+            }
+            else { // raw fp32: the kernel splits in shared memory
+                *reinterpret_cast<float2 *>(Bt_hi + o0) = float2{v.x, -v.y};
+                *reinterpret_cast<float2 *>(Bt_hi + o1) = float2{v.y, v.x};
+            }
         }
+    }
+}
+
+// A' -> (hi, lo), elementwise
+__global__ void __launch_bounds__(256)
+    SplitHiLoKernel(const float4 *__restrict__ in, float4 *__restrict__ hi, float4 *__restrict__ lo, long long n4)
+{
+    const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const float4 v = in[i];
+        const float4 h = make_float4(TfHi(v.x), TfHi(v.y), TfHi(v.z), TfHi(v.w));
+        hi[i] = h;
+        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     }
 }
 
@@ -429,50 +479,100 @@ bool GemmTcEligible(int dtype, int64_t m, int64_t n, int64_t k)
     return tiles < (1ll << 31) && static_cast<double>(m) * n * k >= double(1ll << 24);
 }
 
-size_t GemmTcWorkspaceBytes(int64_t m, int64_t n, int64_t k)
+namespace {
+struct TcWs {
+    size_t a_hi, a_lo, b_hi, b_lo, partial, total;
+};
+// operands split in global memory (PRE) when preparing them is cheap against the GEMM itself
+bool TcPreSplit(int64_t m, int64_t n, int64_t /*k*/) { return m >= 1024 && n >= 1024; }
+TcWs TcWorkspace(int64_t m, int64_t n, int64_t k)
 {
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
     const TcShape t = TcChoose(m, n, k);
-    size_t b = (static_cast<size_t>(16) * n * k + 255) & ~size_t(255); // B'^T
-    if (t.splits > 1)
-        b += static_cast<size_t>(8) * t.splits * m * n; // partial results
-    return b;
+    const bool pre = TcPreSplit(m, n, k);
+    TcWs w;
+    const size_t a_bytes = pre ? align(static_cast<size_t>(8) * m * k) : 0;
+    const size_t b_bytes = align(static_cast<size_t>(16) * n * k); // one B'^T array (2N x 2K floats)
+    w.a_hi = 0;
+    w.a_lo = w.a_hi + a_bytes;
+    w.b_hi = w.a_lo + a_bytes;
+    w.b_lo = w.b_hi + b_bytes;
+    w.partial = w.b_lo + (pre ? b_bytes : 0);
+    w.total = w.partial + (t.splits > 1 ? static_cast<size_t>(8) * t.splits * m * n : 0);
+    return w;
 }
+} // namespace
 
-// C(MxN) = A(MxK) * B(KxN), complex64 row-major; ws holds B'^T (16*N*K bytes) and the split-K partials
+size_t GemmTcWorkspaceBytes(int64_t m, int64_t n, int64_t k) { return TcWorkspace(m, n, k).total; }
+
+// C(MxN) = A(MxK) * B(KxN), complex64 row-major; ws holds A'_hi, A'_lo, B'^T_hi, B'^T_lo and the split-K partials
 int LaunchGemmTc(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
                  cudaStream_t stream)
 {
     JB_REQUIRE(GemmTcEligible(JB_C64, m, n, k), "gemm: shape not eligible for the tensor-core kernel");
-    JB_REQUIRE(ws != nullptr && ws_bytes >= GemmTcWorkspaceBytes(m, n, k), "gemm: tensor-core workspace too small");
+    const TcWs w = TcWorkspace(m, n, k);
+    JB_REQUIRE(ws != nullptr && ws_bytes >= w.total, "gemm: tensor-core workspace too small");
+    const bool pre = TcPreSplit(m, n, k);
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(GemmTf32x3Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        attr_err = cudaFuncSetAttribute(GemmTf32x3Kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kTcSmemBytes));
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(GemmTf32x3Kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(kTcSmemBytes));
     });
     JB_CUDA(attr_err);
+    unsigned char *wb = static_cast<unsigned char *>(ws);
+    float *a_hi = reinterpret_cast<float *>(wb + w.a_hi), *a_lo = reinterpret_cast<float *>(wb + w.a_lo);
+    float *b_hi = reinterpret_cast<float *>(wb + w.b_hi), *b_lo = reinterpret_cast<float *>(wb + w.b_lo);
     dim3 eg(static_cast<unsigned>((n + 31) / 32), static_cast<unsigned>((k + 31) / 32));
-    ExpandBKernel<<<eg, 256, 0, stream>>>(static_cast<const float2 *>(b), static_cast<float *>(ws), k, n);
-    JB_CUDA(cudaGetLastError());
+    if (pre) {
+        ExpandBKernel<true><<<eg, 256, 0, stream>>>(static_cast<const float2 *>(b), b_hi, b_lo, k, n);
+        JB_CUDA(cudaGetLastError());
+        const long long n4 = m * k / 2; // float4 = two complex64 (k % 16 == 0)
+        const int sgrid = static_cast<int>(std::min<long long>((n4 + 255) / 256, NumSMs() * 16ll));
+        SplitHiLoKernel<<<sgrid, 256, 0, stream>>>(static_cast<const float4 *>(a), reinterpret_cast<float4 *>(a_hi),
+                                                   reinterpret_cast<float4 *>(a_lo), n4);
+        JB_CUDA(cudaGetLastError());
+    }
+    else {
+        ExpandBKernel<false><<<eg, 256, 0, stream>>>(static_cast<const float2 *>(b), b_hi, nullptr, k, n);
+        JB_CUDA(cudaGetLastError());
+    }
     const TcShape t = TcChoose(m, n, k);
     const uint32_t box_a = static_cast<uint32_t>(std::min<int64_t>(kTcBM, m));
     const uint32_t box_b = static_cast<uint32_t>(std::min<int64_t>(kTcBN, 2 * n));
-    CUtensorMap map_a, map_b;
-    JB_TRY(MakeMap(&map_a, a, static_cast<uint64_t>(m), static_cast<uint64_t>(2 * k), box_a));
-    JB_TRY(MakeMap(&map_b, ws, static_cast<uint64_t>(2 * n), static_cast<uint64_t>(2 * k), box_b));
-    const uint32_t tx_bytes = (box_a + box_b) * kTcBK * 4;
+    CUtensorMap map_a, map_a_lo, map_b, map_b_lo;
+    JB_TRY(MakeMap(&map_a, pre ? a_hi : a, static_cast<uint64_t>(m), static_cast<uint64_t>(2 * k), box_a));
+    JB_TRY(MakeMap(&map_b, b_hi, static_cast<uint64_t>(2 * n), static_cast<uint64_t>(2 * k), box_b));
+    if (pre) {
+        JB_TRY(MakeMap(&map_a_lo, a_lo, static_cast<uint64_t>(m), static_cast<uint64_t>(2 * k), box_a));
+        JB_TRY(MakeMap(&map_b_lo, b_lo, static_cast<uint64_t>(2 * n), static_cast<uint64_t>(2 * k), box_b));
+    }
+    else {
+        map_a_lo = map_a;
+        map_b_lo = map_b;
+    }
+    const uint32_t tx_bytes = (pre ? 2u : 1u) * (box_a + box_b) * kTcBK * 4;
     float *dst = static_cast<float *>(c);
     float *partial = nullptr;
     if (t.splits > 1) {
-        partial = reinterpret_cast<float *>(static_cast<unsigned char *>(ws) +
-                                            ((static_cast<size_t>(16) * n * k + 255) & ~size_t(255)));
+        partial = reinterpret_cast<float *>(wb + w.partial);
         dst = partial;
     }
     const long long tiles = t.tiles_m * t.tiles_n;
     dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(t.splits), 1);
-    GemmTf32x3Kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(
-        map_a, map_b, dst, static_cast<int>(2 * n), static_cast<int>(t.k_blocks), static_cast<int>(t.k_blocks_per_split),
-        static_cast<int>(t.tiles_n), static_cast<int>(m), tx_bytes, static_cast<long long>(2) * m * n);
+    if (pre)
+        GemmTf32x3Kernel<true><<<grid, TcThreads<true>(), kTcSmemBytes, stream>>>(
+            map_a, map_a_lo, map_b, map_b_lo, dst, static_cast<int>(2 * n), static_cast<int>(t.k_blocks),
+            static_cast<int>(t.k_blocks_per_split), static_cast<int>(t.tiles_n), static_cast<int>(m), tx_bytes,
+            static_cast<long long>(2) * m * n);
+    else
+        GemmTf32x3Kernel<false><<<grid, TcThreads<false>(), kTcSmemBytes, stream>>>(
+            map_a, map_a_lo, map_b, map_b_lo, dst, static_cast<int>(2 * n), static_cast<int>(t.k_blocks),
+            static_cast<int>(t.k_blocks_per_split), static_cast<int>(t.tiles_n), static_cast<int>(m), tx_bytes,
+            static_cast<long long>(2) * m * n);
     JB_CUDA(cudaGetLastError());
     if (t.splits > 1) {
         const long long n4 = m * n / 2; // float4 = two complex64

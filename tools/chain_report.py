@@ -68,9 +68,10 @@ for s, (a, b, c, k) in enumerate(steps):
         total_step += info_ok.step_bytes
         total_fused += info_ok.bytes
         launches += 1
+        kn = " ".join(f"{int(math.log2(steps[c][3]))}:{int(math.log2(size(steps[c][1] if steps[c][0] in (x0,) or size(steps[c][0]) >= size(steps[c][1]) else steps[c][0]) // steps[c][3]))}" for c in chain)
         print(f"chain of {len(chain):2d} at step {chain[0]:3d}: log2|X0|={int(math.log2(size(x0))):2d} -> "
               f"log2|Xk|={int(math.log2(size(steps[chain[-1]][2]))):2d}  tile 2^{info_ok.log_tile:2d} "
-              f"cf={info_ok.conflict_free} stages={info_ok.n_stages}  bytes {info_ok.step_bytes / 1e9:7.3f} -> {info_ok.bytes / 1e9:7.3f} GB")
+              f"cf={info_ok.conflict_free} stages={info_ok.n_stages} logK:logN [{kn}]  bytes {info_ok.step_bytes / 1e9:7.3f} -> {info_ok.bytes / 1e9:7.3f} GB")
     else:
         taken.add(s)
         bts = eb * (size(a) + size(b) + size(c))
