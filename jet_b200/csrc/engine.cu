@@ -97,7 +97,10 @@ struct SliceLeafDesc {
     int n_rem, n_sl;
     long long rem_ext[kSliceMaxRem], rem_stride[kSliceMaxRem];
     long long sl_div[kSliceMaxSl], sl_dim[kSliceMaxSl], sl_stride[kSliceMaxSl];
+    int pow2;                    // every remaining extent is a power of two: digits by shift and mask
+    int rem_shift[kSliceMaxRem]; // bit position of digit j in the view's element index (pow2 only)
 };
+constexpr int kSliceChunk = 1024; // view elements per CTA of SliceLeavesKernel
 
 struct DeviceState {
     long long next_id;  // slice id of the next graph launch (sequential mode)
@@ -110,17 +113,31 @@ __device__ __forceinline__ long long CurrentSlice(const DeviceState *st, const l
     return st->list_pos >= 0 ? list[st->list_pos] : st->next_id;
 }
 
+// grid (descriptors, chunks of kSliceChunk view elements)
 template <typename V>
 __global__ void __launch_bounds__(128)
     SliceLeavesKernel(V *__restrict__ arena, const SliceLeafDesc *__restrict__ descs,
                       const DeviceState *__restrict__ st, const long long *__restrict__ list)
 {
     const SliceLeafDesc &d = descs[blockIdx.x];
+    const long long e0 = static_cast<long long>(blockIdx.y) * kSliceChunk;
+    if (e0 >= d.out_elems)
+        return;
+    const long long e1 = min(d.out_elems, e0 + kSliceChunk);
     const long long sid = CurrentSlice(st, list);
     long long base = d.src_off;
     for (int s = 0; s < d.n_sl; s++)
         base += ((sid / d.sl_div[s]) % d.sl_dim[s]) * d.sl_stride[s];
-    for (long long e = threadIdx.x; e < d.out_elems; e += blockDim.x) {
+    if (d.pow2) {
+        for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+            long long off = base;
+            for (int j = 0; j < d.n_rem; j++)
+                off += ((e >> d.rem_shift[j]) & (d.rem_ext[j] - 1)) * d.rem_stride[j];
+            arena[d.dst_off + e] = arena[off];
+        }
+        return;
+    }
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         long long rem = e, off = base;
         for (int j = d.n_rem - 1; j >= 0; j--) {
             off += (rem % d.rem_ext[j]) * d.rem_stride[j];
@@ -171,7 +188,10 @@ struct Node {
     bool slice_dep = false; // depends on the slice id
     bool is_leaf = false;
     size_t offset = 0; // byte offset in the arena of the tensor the steps read
-    size_t raw_offset = 0; // leaves: byte offset of the unsliced data
+    size_t raw_offset = 0; // leaves / deferred roots: byte offset of the unsliced data
+    bool is_view = false;  // deferred root: `offset` is the per-slice view of the shared tensor at raw_offset
+    int64_t raw_elems = 0; // deferred root: elements of the unsliced tensor
+    int desc = -1;         // index of this node's slice descriptor (sliced leaves and deferred roots)
     int last_use = -1;     // last step (in execution order) reading this node
     bool used_by_slice_step = false;
 };
@@ -251,20 +271,30 @@ int LaunchOp(jb_plan *p, const Op &op)
                           p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream);
 }
 
+int LaunchSliceViews(jb_plan *p)
+{
+    if (p->slice_descs.empty())
+        return 0;
+    long long max_out = 1;
+    for (const SliceLeafDesc &sd : p->slice_descs)
+        max_out = std::max(max_out, sd.out_elems);
+    const dim3 n(static_cast<unsigned>(p->slice_descs.size()),
+                 static_cast<unsigned>((max_out + kSliceChunk - 1) / kSliceChunk), 1);
+    if (p->dtype == JB_C64)
+        SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off),
+                                                          p->At<DeviceState>(p->state_off),
+                                                          p->At<long long>(p->list_off));
+    else
+        SliceLeavesKernel<uint4><<<n, 128, 0, p->stream>>>(p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off),
+                                                          p->At<DeviceState>(p->state_off),
+                                                          p->At<long long>(p->list_off));
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int EnqueueSliceBody(jb_plan *p)
 {
-    if (!p->slice_descs.empty()) {
-        const int n = static_cast<int>(p->slice_descs.size());
-        if (p->dtype == JB_C64)
-            SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(
-                p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off), p->At<DeviceState>(p->state_off),
-                p->At<long long>(p->list_off));
-        else
-            SliceLeavesKernel<uint4><<<n, 128, 0, p->stream>>>(
-                p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off), p->At<DeviceState>(p->state_off),
-                p->At<long long>(p->list_off));
-        JB_CUDA(cudaGetLastError());
-    }
+    JB_TRY(LaunchSliceViews(p));
     for (const Op &op : p->ops)
         JB_TRY(LaunchOp(p, op));
     const bool store = (p->flags & JB_PLAN_STORE_RESULTS) != 0;
@@ -289,8 +319,9 @@ int RunShared(jb_plan *p)
         return 0;
     for (int s : p->shared_order) {
         const Step &st = p->steps[s];
+        const Node &C = p->nodes[st.c];
         JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
-                              p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream));
+                              p->arena + (C.is_view ? C.raw_offset : C.offset), p->arena + p->ws_off, p->stream));
     }
     p->shared_done = true;
     return 0;
@@ -386,6 +417,93 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         return std::find(p->sliced_modes.begin(), p->sliced_modes.end(), m) != p->sliced_modes.end();
     };
 
+    // ---- deferred slicing ------------------------------------------------------------------------
+    // Small subtrees that depend on the slice only through OPEN sliced indices are contracted once,
+    // unsliced (the sliced indices stay ordinary indices inside), in the shared phase; the slice is
+    // selected on the subtree's root, exactly as it is on a leaf.  The reference de-duplicates tasks
+    // that do not depend on the slice at all (TaskBasedContractor.hpp:216-222); this extends it to
+    // tasks whose dependence can be postponed — per slice, only the steps that touch large tensors
+    // remain.  Conditions: no sliced index is contracted inside the subtree (it would become a sum),
+    // every tensor of the unsliced subtree stays small, and the root fits the slice descriptor.
+    const int n_total = d->num_leaves + std::max(d->num_steps, 0);
+    std::vector<char> defer_inside(n_total, 0), defer_root(n_total, 0);
+    const bool defer_enabled = !keep && !(d->flags & JB_PLAN_NO_FUSE) && d->num_sliced > 0 && d->num_steps > 1 && [] {
+        const char *e = getenv("JB_DISABLE_DEFER");
+        return !(e && e[0] == '1');
+    }();
+    if (defer_enabled) {
+        constexpr int64_t kDeferMaxElems = 1 << 14;
+        struct Sym {
+            std::vector<int32_t> modes;
+            int64_t elems = 1, max_elems = 1;
+            bool dep = false, closed = false, ok = false;
+            int a = -1, b = -1;
+        };
+        std::vector<Sym> sym(n_total);
+        bool valid = true;
+        for (int i = 0; i < d->num_leaves; i++) {
+            sym[i].modes = p->nodes[i].modes;
+            sym[i].elems = sym[i].max_elems = p->nodes[i].elems;
+            for (int32_t m : sym[i].modes)
+                sym[i].dep = sym[i].dep || is_sliced(m);
+        }
+        for (int s = 0; s < d->num_steps && valid; s++) {
+            const int a = d->path[2 * s], b = d->path[2 * s + 1], c = d->num_leaves + s;
+            if (a < 0 || b < 0 || a >= c || b >= c || a == b) {
+                valid = false; // reported by the replay below
+                break;
+            }
+            Sym &C = sym[c];
+            C.a = a;
+            C.b = b;
+            C.dep = sym[a].dep || sym[b].dep;
+            C.closed = sym[a].closed || sym[b].closed;
+            for (int32_t m : sym[a].modes) {
+                if (std::find(sym[b].modes.begin(), sym[b].modes.end(), m) == sym[b].modes.end())
+                    C.modes.push_back(m);
+                else if (is_sliced(m))
+                    C.closed = true;
+            }
+            for (int32_t m : sym[b].modes)
+                if (std::find(sym[a].modes.begin(), sym[a].modes.end(), m) == sym[a].modes.end())
+                    C.modes.push_back(m);
+            for (int32_t m : C.modes)
+                C.elems *= mode_dim[m];
+            C.max_elems = std::max({C.elems, sym[a].max_elems, sym[b].max_elems});
+            int n_sl = 0, n_rem = 0;
+            for (int32_t m : C.modes)
+                (is_sliced(m) ? n_sl : n_rem)++;
+            C.ok = C.dep && !C.closed && C.max_elems <= kDeferMaxElems && n_sl >= 1 && n_sl <= kSliceMaxSl &&
+                   n_rem <= kSliceMaxRem && static_cast<int>(C.modes.size()) <= JB_MAX_RANK;
+        }
+        if (valid) {
+            std::vector<int> consumer(n_total, -1);
+            for (int s = 0; s < d->num_steps; s++) {
+                consumer[d->path[2 * s]] = d->num_leaves + s;
+                consumer[d->path[2 * s + 1]] = d->num_leaves + s;
+            }
+            const int last = n_total - 1;
+            for (int c = d->num_leaves; c < n_total; c++) {
+                if (!sym[c].ok || c == last)
+                    continue;
+                const int up_node = consumer[c];
+                if (up_node >= 0 && up_node != last && sym[up_node].ok)
+                    continue; // not maximal
+                defer_root[c] = 1;
+                std::vector<int> stack = {sym[c].a, sym[c].b};
+                while (!stack.empty()) {
+                    const int v = stack.back();
+                    stack.pop_back();
+                    defer_inside[v] = 1;
+                    if (v >= d->num_leaves) {
+                        stack.push_back(sym[v].a);
+                        stack.push_back(sym[v].b);
+                    }
+                }
+            }
+        }
+    }
+
     // ---- arena layout: raw leaves, then sliced views ----------------------------------------------
     OffsetAllocator alloc;
     for (int i = 0; i < d->num_leaves; i++) {
@@ -393,14 +511,15 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         n.raw_offset = alloc.Alloc(n.elems * p->eb);
         n.offset = n.raw_offset;
     }
-    for (int i = 0; i < d->num_leaves; i++) {
-        Node &n = p->nodes[i];
+    // turns node n (unsliced layout) into its per-slice view: descriptor + view buffer; the node's
+    // modes / extents / elems become those of the view.  src_off is filled in by the caller.
+    auto make_view = [&](Node &n) -> int {
         std::vector<int> sl_axes;
         for (size_t j = 0; j < n.modes.size(); j++)
             if (is_sliced(n.modes[j]))
                 sl_axes.push_back(static_cast<int>(j));
         if (sl_axes.empty())
-            continue;
+            return 0;
         n.slice_dep = true;
         SliceLeafDesc sd;
         std::memset(&sd, 0, sizeof(sd));
@@ -438,14 +557,31 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             }
         }
         sd.out_elems = out_elems;
+        sd.pow2 = 1;
+        {
+            int shift = 0;
+            for (int j = sd.n_rem - 1; j >= 0; j--) {
+                sd.rem_shift[j] = shift;
+                if (!IsPow2(sd.rem_ext[j]))
+                    sd.pow2 = 0;
+                else
+                    shift += Log2(sd.rem_ext[j]);
+            }
+        }
         sd.src_off = static_cast<long long>(n.raw_offset / p->eb);
+        n.raw_elems = n.elems;
         n.offset = alloc.Alloc(out_elems * p->eb);
         sd.dst_off = static_cast<long long>(n.offset / p->eb);
         n.modes = new_modes;
         n.extent = new_ext;
         n.elems = out_elems;
+        n.desc = static_cast<int>(p->slice_descs.size());
         p->slice_descs.push_back(sd);
-    }
+        return 0;
+    };
+    for (int i = 0; i < d->num_leaves; i++)
+        if (!defer_inside[i])
+            JB_TRY(make_view(p->nodes[i]));
 
     // ---- steps: symbolic replay of the path (include/jet/PathInfo.hpp:262-297) --------------------
     JB_REQUIRE(d->num_steps >= 0, "plan: negative step count");
@@ -470,6 +606,12 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         C.extent = st.cp.extent_c;
         C.elems = st.cp.m * st.cp.n;
         C.slice_dep = !st.shared;
+        if (defer_root[cur] && st.shared) {
+            // the step writes the unsliced tensor (shared phase); consumers read its per-slice view
+            C.is_view = true;
+            JB_TRY(make_view(C)); // src_off is patched once the unsliced tensor has an arena offset
+            JB_REQUIRE(C.desc >= 0, "plan: internal: deferred root without sliced index");
+        }
         p->nodes.push_back(C);
         p->steps.push_back(st);
     }
@@ -621,13 +763,19 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     p->chain_stage_off = alloc.Alloc(ChainStagingBytes());
     for (size_t e = 0; e < exec.size(); e++) {
         Node &C = p->nodes[exec[e].out];
-        C.offset = alloc.Alloc(C.elems * p->eb);
+        if (C.is_view) { // the view buffer exists already; the unsliced tensor lives for the whole run
+            C.raw_offset = alloc.Alloc(C.raw_elems * p->eb);
+            p->slice_descs[C.desc].src_off = static_cast<long long>(C.raw_offset / p->eb);
+        }
+        else {
+            C.offset = alloc.Alloc(C.elems * p->eb);
+        }
         if (keep)
             continue;
         std::set<int> seen;
         for (int in : exec[e].reads) {
             Node &I = p->nodes[in];
-            if (I.is_leaf || I.last_use != static_cast<int>(e) || !seen.insert(in).second)
+            if (I.is_leaf || I.is_view || I.last_use != static_cast<int>(e) || !seen.insert(in).second)
                 continue;
             // a shared tensor read by per-slice steps must survive every slice
             const bool producer_shared = !I.slice_dep;
@@ -673,8 +821,18 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     S.steps_shared = static_cast<int32_t>(p->shared_order.size());
     S.launches_per_slice = (p->slice_descs.empty() ? 0 : 1) + 1;
     for (const Step &st : p->steps) {
-        S.jet_flops_per_slice += 2.0 * double(st.cp.m) * double(st.cp.n) * double(st.cp.k);
-        S.max_step_elems = std::max<int64_t>(S.max_step_elems, st.cp.m * st.cp.n);
+        // Jet-convention flops / memory are those of the SLICED network (PathInfo.hpp:168-182 after
+        // SliceIndices): a step of a deferred subtree carries its open sliced indices in M or N
+        const Node &C = p->nodes[st.c];
+        double unsliced = 1.0;
+        if (C.is_view)
+            unsliced = double(C.raw_elems) / double(C.elems);
+        else
+            for (size_t j = 0; j < C.modes.size(); j++)
+                if (is_sliced(C.modes[j]))
+                    unsliced *= double(C.extent[j]);
+        S.jet_flops_per_slice += 2.0 * double(st.cp.m) * double(st.cp.n) * double(st.cp.k) / unsliced;
+        S.max_step_elems = std::max<int64_t>(S.max_step_elems, static_cast<int64_t>(double(st.cp.m * st.cp.n) / unsliced));
         if (st.shared) {
             S.flops_shared += st.cp.flops();
             S.bytes_shared += st.cp.bytes();
@@ -942,17 +1100,7 @@ int jb_plan_profile_ops(jb_plan *p, int64_t slice, int reps, float *ms, int32_t 
     std::vector<double> total(p->ops.size(), 0.0);
     for (int r = 0; r < reps + 1; r++) {
         SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), slice, -1, 0);
-        if (!p->slice_descs.empty()) {
-            const int n = static_cast<int>(p->slice_descs.size());
-            if (p->dtype == JB_C64)
-                SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(
-                    p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off),
-                    p->At<DeviceState>(p->state_off), p->At<long long>(p->list_off));
-            else
-                SliceLeavesKernel<uint4><<<n, 128, 0, p->stream>>>(
-                    p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off),
-                    p->At<DeviceState>(p->state_off), p->At<long long>(p->list_off));
-        }
+        JB_TRY(LaunchSliceViews(p));
         for (size_t i = 0; i < p->ops.size(); i++) {
             JB_CUDA(cudaEventRecord(ev[i], p->stream));
             JB_TRY(LaunchOp(p, p->ops[i]));
