@@ -76,6 +76,9 @@ int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const 
 // tensor-core (tcgen05, 3xTF32) complex64 GEMM for large aligned shapes (gemm_tc.cu)
 bool GemmDmmaEligible(int dtype, int64_t m, int64_t n, int64_t k); // complex128, FP64 tensor pipe (gemm_dmma.cu)
 size_t GemmDmmaWorkspaceBytes(int64_t m, int64_t n, int64_t k);
+int LaunchGemmDmmaGatherA(int64_t m, int64_t n, int64_t k, const void *a_tensor, const int *free_bits, int n_free,
+                          const int *common_bits, int n_common, const void *b, void *c, void *ws, size_t ws_bytes,
+                          cudaStream_t stream);
 int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
                    cudaStream_t stream);
 bool GemmTcEligible(int dtype, int64_t m, int64_t n, int64_t k);
@@ -100,6 +103,9 @@ struct ContractPlan {
     bool permute_a = false, permute_b = false;
     std::vector<int32_t> perm_a, perm_b;
     size_t ws_a_off = 0, ws_b_off = 0, ws_gemm_off = 0, ws_gemm_bytes = 0;
+    // ttgt, complex128: the DMMA GEMM reads A in its original layout (no permuted copy of A)
+    bool gather_a = false;
+    std::vector<int> a_free_bits, a_common_bits; // address bits of A's free / contracted index bits, ascending
     // stream kernel parameters (opaque blob, see contract.cu)
     std::vector<unsigned char> stream_blob;
     int launches = 1;

@@ -858,6 +858,29 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
     auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
     size_t off = 0;
     P.launches = 1;
+    // complex128 on the DMMA kernel: fold Transpose(A) into the GEMM's tile loads
+    if (P.permute_a && pow2 && dtype == JB_C128 && DmmaEnabled() && GemmDmmaEligible(dtype, P.m, P.n, P.k) &&
+        !SmallMnEligible(P.m, P.n, P.k)) {
+        std::vector<int> lo(rank_a);
+        int nb = 0;
+        for (int i = rank_a - 1; i >= 0; i--) {
+            lo[i] = nb;
+            nb += Log2(extent_a[i]);
+        }
+        auto bits_of = [&](const std::vector<int> &axes, std::vector<int> *out) {
+            out->clear();
+            for (int ax : axes)
+                for (int bbit = 0; bbit < Log2(extent_a[ax]); bbit++)
+                    out->push_back(lo[ax] + bbit);
+            std::sort(out->begin(), out->end());
+        };
+        bits_of(left, &P.a_free_bits);
+        bits_of(common_a, &P.a_common_bits);
+        if (P.a_free_bits.size() <= 40 && P.a_common_bits.size() <= 32 && P.a_common_bits.size() >= 3 && nb <= 62) {
+            P.gather_a = true;
+            P.permute_a = false;
+        }
+    }
     if (P.permute_a) {
         P.ws_a_off = off;
         off += align(eb * static_cast<size_t>(size_a));
@@ -903,6 +926,10 @@ int LaunchContract(const ContractPlan &P, const void *a, const void *b, void *c,
                              P.perm_b.data(), stream));
         bt = w + P.ws_b_off;
     }
+    if (P.gather_a)
+        return LaunchGemmDmmaGatherA(P.m, P.n, P.k, a, P.a_free_bits.data(), static_cast<int>(P.a_free_bits.size()),
+                                     P.a_common_bits.data(), static_cast<int>(P.a_common_bits.size()), bt, c,
+                                     w ? w + P.ws_gemm_off : nullptr, P.ws_gemm_bytes, stream);
     return LaunchGemm(P.dtype, P.m, P.n, P.k, at, bt, c, w ? w + P.ws_gemm_off : nullptr,
                       P.ws_gemm_bytes, stream);
 }

@@ -17,7 +17,9 @@
 //  * Ragged M and N: rows / columns beyond the matrix are zero-filled by cp.async (src-size 0) and
 //    not stored.  K must be a multiple of 8.
 #include <algorithm>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -48,9 +50,25 @@ __device__ __forceinline__ void CpAsync16(unsigned dst, const void *src, bool va
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 
+// GATHER: A is read in its ORIGINAL tensor layout — the Transpose(A -> left ++ common) of
+// Tensor::ContractTensors (reference include/jet/Tensor.hpp:743-746) is folded into the tile loads.
+// All extents are powers of two: logical row bit j / k bit j of the GEMM is address bit m_bit[j] /
+// k_bit[j] of the tensor (both ascending: dropping the contracted bits from A's address leaves the
+// free indices in row-major order).  The 1024 elements of a tile are walked in ascending ADDRESS order
+// (tile_pos / tile_kind / tile_idx: the 7 row bits and 3 k bits of the tile, merged by address), so the
+// 16-byte cp.async of adjacent lanes touch adjacent memory wherever the tensor layout allows.
+struct DmmaGather {
+    int log_m, log_k;
+    unsigned char m_bit[40], k_bit[32];
+    unsigned char tile_pos[10], tile_kind[10], tile_idx[10]; // kind 0: row bit tile_idx, 1: k bit tile_idx
+    int tile_bits;
+};
+
+template <bool GATHER>
 __global__ void __launch_bounds__(kDmThreads, 1)
     GemmDmmaKernel(const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C,
-                   long long M, long long N, long long K, int tiles_n, int k_tiles_per_split)
+                   long long M, long long N, long long K, int tiles_n, int k_tiles_per_split,
+                   const __grid_constant__ DmmaGather ga)
 {
     extern __shared__ __align__(16) double dm_smem[];
     double *As = dm_smem;
@@ -67,15 +85,60 @@ __global__ void __launch_bounds__(kDmThreads, 1)
     const unsigned as_s = static_cast<unsigned>(__cvta_generic_to_shared(As));
     const unsigned bs_s = static_cast<unsigned>(__cvta_generic_to_shared(Bs));
 
+    // GATHER: per-thread constants of its four tile elements, and the CTA's row base
+    long long g_off[4] = {0, 0, 0, 0};
+    unsigned g_dst[4] = {0, 0, 0, 0};
+    bool g_ok[4] = {false, false, false, false};
+    long long g_rowbase = 0;
+    if constexpr (GATHER) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = i * kDmThreads + tid;
+            int row = 0, kc = 0;
+            long long off = 0;
+            for (int j = 0; j < ga.tile_bits; j++)
+                if ((q >> j) & 1) {
+                    off |= 1ll << ga.tile_pos[j];
+                    if (ga.tile_kind[j] == 0)
+                        row |= 1 << ga.tile_idx[j];
+                    else
+                        kc |= 1 << ga.tile_idx[j];
+                }
+            g_ok[i] = q < (1 << ga.tile_bits) && m0 + row < M;
+            g_off[i] = off;
+            g_dst[i] = static_cast<unsigned>(sizeof(double)) * (row * kDmAPitch + kc * 2);
+        }
+        const long long mt = m0 >> 7;
+        for (int j = 7; j < ga.log_m; j++)
+            if ((mt >> (j - 7)) & 1)
+                g_rowbase |= 1ll << ga.m_bit[j];
+    }
+
     auto load_stage = [&](int kt, int s) {
         const long long k0 = static_cast<long long>(kt0 + kt) * kDmBK;
+        if constexpr (GATHER) {
+            long long kbase = g_rowbase;
+            const long long kq = k0 >> 3;
+            for (int j = 3; j < ga.log_k; j++)
+                if ((kq >> (j - 3)) & 1)
+                    kbase |= 1ll << ga.k_bit[j];
+            // (tile elements beyond 2^tile_bits do not exist when M < 128: those shared-memory rows stay
+            // unwritten; they only feed output rows >= M, which are not stored)
 #pragma unroll
-        for (int i = 0; i < (kDmBM * kDmBK) / kDmThreads; i++) { // A: 1024 complex, 4 per thread
-            const int q = i * kDmThreads + tid;
-            const int row = q / kDmBK, kc = q % kDmBK;
-            const bool ok = m0 + row < M;
-            const double2 *src = A + (ok ? (m0 + row) * K + k0 + kc : 0);
-            CpAsync16(as_s + static_cast<unsigned>(sizeof(double)) * (s * kDmAStage + row * kDmAPitch + kc * 2), src, ok);
+            for (int i = 0; i < 4; i++)
+                if (g_ok[i])
+                    CpAsync16(as_s + static_cast<unsigned>(sizeof(double)) * (s * kDmAStage) + g_dst[i],
+                              A + kbase + g_off[i], true);
+        }
+        else {
+#pragma unroll
+            for (int i = 0; i < (kDmBM * kDmBK) / kDmThreads; i++) { // A: 1024 complex, 4 per thread
+                const int q = i * kDmThreads + tid;
+                const int row = q / kDmBK, kc = q % kDmBK;
+                const bool ok = m0 + row < M;
+                const double2 *src = A + (ok ? (m0 + row) * K + k0 + kc : 0);
+                CpAsync16(as_s + static_cast<unsigned>(sizeof(double)) * (s * kDmAStage + row * kDmAPitch + kc * 2), src, ok);
+            }
         }
 #pragma unroll
         for (int i = 0; i < (kDmBK * kDmBN) / kDmThreads; i++) { // B: 512 complex, 2 per thread
@@ -213,15 +276,65 @@ size_t GemmDmmaWorkspaceBytes(int64_t m, int64_t n, int64_t k)
     return t.splits > 1 ? sizeof(double2) * static_cast<size_t>(t.splits) * m * n : 0;
 }
 
+namespace {
+int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
+               const DmmaGather *ga, cudaStream_t stream);
+}
+
 int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
                    cudaStream_t stream)
+{
+    return LaunchDmma(m, n, k, a, b, c, ws, ws_bytes, nullptr, stream);
+}
+
+// A in its original tensor layout: free_bits / common_bits = address bits (element units, ascending) of
+// the free and of the contracted index bits of A
+int LaunchGemmDmmaGatherA(int64_t m, int64_t n, int64_t k, const void *a_tensor, const int *free_bits, int n_free,
+                          const int *common_bits, int n_common, const void *b, void *c, void *ws, size_t ws_bytes,
+                          cudaStream_t stream)
+{
+    JB_REQUIRE((int64_t(1) << n_free) == m && (int64_t(1) << n_common) == k, "gemm: gather layout does not match M, K");
+    JB_REQUIRE(n_free <= 40 && n_common <= 32 && n_common >= 3, "gemm: gather layout out of range");
+    DmmaGather ga;
+    std::memset(&ga, 0, sizeof(ga));
+    ga.log_m = n_free;
+    ga.log_k = n_common;
+    for (int j = 0; j < n_free; j++)
+        ga.m_bit[j] = static_cast<unsigned char>(free_bits[j]);
+    for (int j = 0; j < n_common; j++)
+        ga.k_bit[j] = static_cast<unsigned char>(common_bits[j]);
+    // tile bits (<= 7 row bits, 3 k bits) merged in ascending address order
+    struct TB {
+        int pos, kind, idx;
+    };
+    std::vector<TB> tb;
+    for (int j = 0; j < std::min(n_free, 7); j++)
+        tb.push_back({free_bits[j], 0, j});
+    for (int j = 0; j < 3; j++)
+        tb.push_back({common_bits[j], 1, j});
+    std::sort(tb.begin(), tb.end(), [](const TB &x, const TB &y) { return x.pos < y.pos; });
+    ga.tile_bits = static_cast<int>(tb.size());
+    for (size_t j = 0; j < tb.size(); j++) {
+        ga.tile_pos[j] = static_cast<unsigned char>(tb[j].pos);
+        ga.tile_kind[j] = static_cast<unsigned char>(tb[j].kind);
+        ga.tile_idx[j] = static_cast<unsigned char>(tb[j].idx);
+    }
+    return LaunchDmma(m, n, k, a_tensor, b, c, ws, ws_bytes, &ga, stream);
+}
+
+namespace {
+int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
+               const DmmaGather *gather, cudaStream_t stream)
 {
     JB_REQUIRE(GemmDmmaEligible(JB_C128, m, n, k), "gemm: shape not eligible for the FP64 tensor-core kernel");
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(GemmDmmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        attr_err = cudaFuncSetAttribute(GemmDmmaKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kDmSmemBytes));
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(GemmDmmaKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(kDmSmemBytes));
     });
     JB_CUDA(attr_err);
     const DmmaShape t = DmmaChoose(m, n, k);
@@ -231,9 +344,16 @@ int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b
         dst = static_cast<double2 *>(ws);
     }
     dim3 grid(static_cast<unsigned>(t.tiles), static_cast<unsigned>(t.splits), 1);
-    GemmDmmaKernel<<<grid, kDmThreads, kDmSmemBytes, stream>>>(static_cast<const double2 *>(a),
-                                                               static_cast<const double2 *>(b), dst, m, n, k, t.tiles_n,
-                                                               t.k_tiles_per_split);
+    DmmaGather none;
+    std::memset(&none, 0, sizeof(none));
+    if (gather != nullptr)
+        GemmDmmaKernel<true><<<grid, kDmThreads, kDmSmemBytes, stream>>>(
+            static_cast<const double2 *>(a), static_cast<const double2 *>(b), dst, m, n, k, t.tiles_n,
+            t.k_tiles_per_split, *gather);
+    else
+        GemmDmmaKernel<false><<<grid, kDmThreads, kDmSmemBytes, stream>>>(
+            static_cast<const double2 *>(a), static_cast<const double2 *>(b), dst, m, n, k, t.tiles_n,
+            t.k_tiles_per_split, none);
     JB_CUDA(cudaGetLastError());
     if (t.splits > 1) {
         const long long mn = m * n;
@@ -244,5 +364,6 @@ int LaunchGemmDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b
     }
     return 0;
 }
+} // namespace
 
 } // namespace jb

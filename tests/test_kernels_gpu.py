@@ -312,6 +312,24 @@ def test_contract_c128_compute_bound_step_uses_ttgt_dmma(ops):
     assert rel_err(out, ref) < 1e-12
 
 
+def test_contract_c128_gather_dmma_random_layouts(ops):
+    """complex128 TTGT steps read A in its original layout (the DMMA kernel folds Transpose(A) into its
+    tile loads): random positions of the contracted indices, dims 2 / 4 / 8, ragged M (< 128 rows)."""
+    rng = np.random.default_rng(50)
+    for dims, ra, nc, nf in [(2, 18, 6, 6), (2, 14, 5, 7), (4, 9, 3, 3), (8, 6, 2, 2), (2, 12, 6, 6), (2, 13, 5, 5)]:
+        ia = list(range(ra))
+        common = sorted(rng.choice(ra, nc, replace=False).tolist())
+        ib = common + list(range(100, 100 + nf))
+        ib = [ib[i] for i in rng.permutation(len(ib))]
+        a = rand_c(rng, dims ** ra, np.complex128).reshape([dims] * ra)
+        b = rand_c(rng, dims ** len(ib), np.complex128).reshape([dims] * len(ib))
+        info = ops.contract_info(np.complex128, a.shape, ia, b.shape, ib)
+        assert info.kernel == 1, (dims, ra, nc, nf)
+        out, _ = ops.contract(a, ia, b, ib)
+        _, ref = jo.contract(([str(i) for i in ia], a), ([str(i) for i in ib], b))
+        assert rel_err(out, ref) < 1e-12, (dims, ra, nc, nf, rel_err(out, ref))
+
+
 def test_gemm_tensor_core_exact_on_small_integers(ops):
     """Integer data: every partial product and sum is exact in FP32, so the tensor-core path must
     reproduce the integer result bit for bit (catches layout / swizzle / sign errors)."""
