@@ -248,7 +248,14 @@ struct jb_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool shared_done = false;
     bool have_run = false;
-    long long *h_list = nullptr;
+    long long *h_list = nullptr;   // two halves of list_cap ids, used alternately
+    cudaEvent_t ev_list[2] = {nullptr, nullptr};
+    int list_half = 0;
+    // upload staging: the raw leaves are contiguous at the start of the arena; small networks are
+    // uploaded as ONE copy from a pinned mirror instead of one copy per leaf
+    unsigned char *h_stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_stage = nullptr;
     jb_plan_stats_t stats;
 
     template <typename T> T *At(size_t off) const { return reinterpret_cast<T *>(arena + off); }
@@ -798,7 +805,23 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     JB_CUDA(cudaEventCreate(&p->ev0));
     JB_CUDA(cudaEventCreate(&p->ev1));
-    JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_list), sizeof(long long) * p->list_cap));
+    JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_list), sizeof(long long) * p->list_cap * 2));
+    for (auto &e : p->ev_list)
+        JB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        size_t end = 0;
+        for (int i = 0; i < p->num_leaves; i++) {
+            const Node &n = p->nodes[i];
+            end = std::max(end, n.raw_offset + static_cast<size_t>(n.desc >= 0 ? n.raw_elems : n.elems) * p->eb);
+        }
+        constexpr size_t kStageMax = size_t(32) << 20;
+        if (end > 0 && end <= kStageMax && p->num_leaves > 1) {
+            p->stage_bytes = end;
+            JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_stage), end));
+            std::memset(p->h_stage, 0, end);
+            JB_CUDA(cudaEventCreateWithFlags(&p->ev_stage, cudaEventDisableTiming));
+        }
+    }
     if (!p->slice_descs.empty())
         JB_CUDA(cudaMemcpyAsync(p->arena + p->descs_off, p->slice_descs.data(),
                                 sizeof(SliceLeafDesc) * p->slice_descs.size(), cudaMemcpyHostToDevice,
@@ -891,6 +914,13 @@ int jb_plan_destroy(jb_plan *p)
         cudaStreamDestroy(p->stream);
     if (p->h_list)
         cudaFreeHost(p->h_list);
+    for (auto &e : p->ev_list)
+        if (e)
+            cudaEventDestroy(e);
+    if (p->h_stage)
+        cudaFreeHost(p->h_stage);
+    if (p->ev_stage)
+        cudaEventDestroy(p->ev_stage);
     if (p->arena)
         cudaFree(p->arena);
     if (p->chain_slot >= 0)
@@ -910,20 +940,21 @@ int jb_plan_upload(jb_plan *p, const void *const *h_data)
 {
     JB_REQUIRE(p && h_data, "plan: null argument");
     JB_CUDA(cudaSetDevice(p->device));
+    if (p->h_stage != nullptr)
+        JB_CUDA(cudaEventSynchronize(p->ev_stage)); // the previous upload has left the pinned mirror
     for (int i = 0; i < p->num_leaves; i++) {
         const Node &n = p->nodes[i];
-        // raw (unsliced) element count
-        size_t raw_elems = n.elems;
-        if (n.slice_dep) {
-            for (const auto &sd : p->slice_descs)
-                if (static_cast<size_t>(sd.dst_off) * p->eb == n.offset) {
-                    for (int s = 0; s < sd.n_sl; s++)
-                        raw_elems *= sd.sl_dim[s];
-                }
-        }
+        const size_t raw_elems = static_cast<size_t>(n.desc >= 0 ? n.raw_elems : n.elems); // unsliced
         JB_REQUIRE(h_data[i] != nullptr, "plan: null leaf data");
-        JB_CUDA(cudaMemcpyAsync(p->arena + n.raw_offset, h_data[i], raw_elems * p->eb,
-                                cudaMemcpyHostToDevice, p->stream));
+        if (p->h_stage != nullptr)
+            std::memcpy(p->h_stage + n.raw_offset, h_data[i], raw_elems * p->eb);
+        else
+            JB_CUDA(cudaMemcpyAsync(p->arena + n.raw_offset, h_data[i], raw_elems * p->eb,
+                                    cudaMemcpyHostToDevice, p->stream));
+    }
+    if (p->h_stage != nullptr) {
+        JB_CUDA(cudaMemcpyAsync(p->arena, p->h_stage, p->stage_bytes, cudaMemcpyHostToDevice, p->stream));
+        JB_CUDA(cudaEventRecord(p->ev_stage, p->stream));
     }
     p->shared_done = false;
     return 0;
@@ -954,13 +985,19 @@ int jb_plan_run_list(jb_plan *p, const int64_t *ids, int64_t count)
     for (int64_t i = 0; i < count; i++)
         JB_REQUIRE(ids[i] >= 0 && ids[i] < p->num_slices, "plan: slice id out of bounds");
     JB_CUDA(cudaSetDevice(p->device));
-    // the pinned staging buffer may still be in flight from an earlier call
-    JB_CUDA(cudaStreamSynchronize(p->stream));
+    // Two pinned halves used alternately: the copy out of a half may still be in flight from the call
+    // before last (waited on through its event); the device-side list itself is rewritten in stream
+    // order, after the slices of the previous call have consumed it.
+    const int half = p->list_half;
+    p->list_half ^= 1;
+    JB_CUDA(cudaEventSynchronize(p->ev_list[half]));
+    long long *h = p->h_list + static_cast<size_t>(half) * p->list_cap;
     for (int64_t i = 0; i < count; i++)
-        p->h_list[i] = ids[i];
+        h[i] = ids[i];
     if (count > 0)
-        JB_CUDA(cudaMemcpyAsync(p->arena + p->list_off, p->h_list, sizeof(long long) * count,
-                                cudaMemcpyHostToDevice, p->stream));
+        JB_CUDA(cudaMemcpyAsync(p->arena + p->list_off, h, sizeof(long long) * count, cudaMemcpyHostToDevice,
+                                p->stream));
+    JB_CUDA(cudaEventRecord(p->ev_list[half], p->stream));
     return RunSlices(p, 0, 0, count);
 }
 
