@@ -245,6 +245,8 @@ struct jb_plan {
     cudaStream_t stream = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t shared_graph = nullptr; // the slice-independent steps
+    cudaGraphExec_t shared_exec = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool shared_done = false;
     bool have_run = false;
@@ -320,16 +322,47 @@ int EnqueueSliceBody(jb_plan *p)
     return 0;
 }
 
-int RunShared(jb_plan *p)
+int EnqueueShared(jb_plan *p)
 {
-    if (p->shared_done)
-        return 0;
     for (int s : p->shared_order) {
         const Step &st = p->steps[s];
         const Node &C = p->nodes[st.c];
         JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
                               p->arena + (C.is_view ? C.raw_offset : C.offset), p->arena + p->ws_off, p->stream));
     }
+    return 0;
+}
+
+// The slice-independent steps (and the deferred subtrees) run once per reset / upload; they are mostly
+// tiny, so they too are replayed from a CUDA graph (hundreds of launches otherwise).
+int RunShared(jb_plan *p)
+{
+    if (p->shared_done)
+        return 0;
+    if (p->shared_order.empty()) {
+        p->shared_done = true;
+        return 0;
+    }
+    if (p->flags & JB_PLAN_NO_GRAPH) {
+        JB_TRY(EnqueueShared(p));
+        p->shared_done = true;
+        return 0;
+    }
+    if (p->shared_exec == nullptr) {
+        JB_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = EnqueueShared(p);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
+        if (rc != 0) {
+            if (g)
+                cudaGraphDestroy(g);
+            return rc;
+        }
+        JB_CUDA(ce);
+        p->shared_graph = g;
+        JB_CUDA(cudaGraphInstantiate(&p->shared_exec, p->shared_graph, 0));
+    }
+    JB_CUDA(cudaGraphLaunch(p->shared_exec, p->stream));
     p->shared_done = true;
     return 0;
 }
@@ -906,6 +939,10 @@ int jb_plan_destroy(jb_plan *p)
         cudaGraphExecDestroy(p->graph_exec);
     if (p->graph)
         cudaGraphDestroy(p->graph);
+    if (p->shared_exec)
+        cudaGraphExecDestroy(p->shared_exec);
+    if (p->shared_graph)
+        cudaGraphDestroy(p->shared_graph);
     if (p->ev0)
         cudaEventDestroy(p->ev0);
     if (p->ev1)
