@@ -273,19 +273,20 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
                 gpos.push_back(pos[b]);
         std::sort(gpos.begin(), gpos.end());
         sp[i].g = gpos;
-        const bool in_place = !S[i].empty() && S[i].size() == F[i].size();
-        if (in_place) {
-            // k bit q <-> the contracted bit at the q-th lowest tile position; the q-th new bit
-            // takes over exactly that position (lets a run of such steps stay in registers)
+        // A step that creates no more bits than it contracts reuses the contracted positions: k bit q <->
+        // the contracted bit at the q-th lowest tile position, the q-th new bit takes over exactly that
+        // position, and positions left over (K > N: the tensor shrinks) die.  Such steps can run in a
+        // register stage: the matrix is padded to K x K with zero columns, the dead positions hold zeros.
+        const bool in_place = !S[i].empty() && F[i].size() <= S[i].size();
+        if (in_place)
             std::sort(S[i].begin(), S[i].end(), [&](int x, int y) { return pos[x] < pos[y]; });
-        }
         for (int b : S[i]) {
             sp[i].k.push_back(pos[b]);
             alive.erase(b);
         }
         for (size_t q = 0; q < S[i].size(); q++) {
             const int b = S[i][q];
-            if (!in_place)
+            if (!in_place || q >= F[i].size())
                 free_pos.insert(pos[b]);
             pos.erase(b);
         }
@@ -310,7 +311,9 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
         Q.log_k = static_cast<uint8_t>(S[i].size());
         Q.log_n = static_cast<uint8_t>(F[i].size());
         Q.log_g = static_cast<uint8_t>(gpos.size());
-        Q.np = static_cast<uint16_t>(std::max(4, 1 << Q.log_n));
+        // row stride of the K x np matrix: N rounded up to 4; K for position-reusing steps (K >= N), whose
+        // register-stage form is a square matrix with zero columns beyond N
+        Q.np = static_cast<uint16_t>(std::max(4, 1 << (in_place ? Q.log_k : Q.log_n)));
         Q.b_off = static_cast<uint16_t>(resident);
         resident += (1 << Q.log_k) * Q.np;
         for (size_t q = 0; q < S[i].size(); q++) {

@@ -165,8 +165,10 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                                     if (mask & (1 << b))
                                         mpos.push_back(b);
                                 const int K = 1 << mpos.size();
-                                if (static_cast<int>(mpos.size()) != q.log_k || q.log_k != q.log_n)
+                                if (static_cast<int>(mpos.size()) != q.log_k || q.log_n > q.log_k ||
+                                    q.np != std::max(4, K))
                                     hazards += 1000; // planner inconsistency
+                                const int N = 1 << q.log_n; // N < K: the matrix has zero columns beyond N
                                 auto spread = [&](int v) {
                                     int r = 0;
                                     for (size_t b = 0; b < mpos.size(); b++)
@@ -178,7 +180,7 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
                                 for (int g = 0; g < NE; g++) {
                                     if (g & mask)
                                         continue;
-                                    for (int n = 0; n < K; n++)
+                                    for (int n = 0; n < N; n++)
                                         for (int k = 0; k < K; k++)
                                             out[g | spread(n)] += E[g | spread(k)] * Bm[q.b_off + k * q.np + n];
                                 }
