@@ -103,6 +103,10 @@ struct ContractPlan {
     bool permute_a = false, permute_b = false;
     std::vector<int32_t> perm_a, perm_b;
     size_t ws_a_off = 0, ws_b_off = 0, ws_gemm_off = 0, ws_gemm_bytes = 0;
+    // ttgt, complex64: C^T = B^T A^T — the large operand B plays the GEMM's A role (read as it is, full
+    // 128-row tiles) and the small A is the one expanded to B'; the small C^T is transposed at the end
+    bool swap_roles = false;
+    size_t ws_ct_off = 0;
     // ttgt, complex128: the DMMA GEMM reads A in its original layout (no permuted copy of A)
     bool gather_a = false;
     std::vector<int> a_free_bits, a_common_bits; // address bits of A's free / contracted index bits, ascending

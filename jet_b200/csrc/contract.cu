@@ -841,14 +841,32 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
     P.kernel = 1;
     P.perm_a.clear();
     P.perm_b.clear();
-    for (int i : left)
-        P.perm_a.push_back(i);
-    for (int i : common_a)
-        P.perm_a.push_back(i);
-    for (int j : common_b)
-        P.perm_b.push_back(j);
-    for (int j : right)
-        P.perm_b.push_back(j);
+    // complex64, short M and a long N: the tensor-core GEMM wastes most of its 128-row tile on M, and its
+    // B' expansion quadruples the traffic of the LARGE operand.  Compute C^T = B^T A^T instead: B (as
+    // right ++ common) is the GEMM's row operand, A (as common ++ left) the expanded one, and the small
+    // C^T (N x M) is transposed into C at the end.
+    P.swap_roles = dtype == JB_C64 && TcEnabled() && P.m < 128 && P.n >= 1024 && size_b >= 8 * size_a &&
+                   GemmTcEligible(dtype, P.n, P.m, P.k) && !SmallMnEligible(P.m, P.n, P.k);
+    if (P.swap_roles) {
+        for (int i : common_a)
+            P.perm_a.push_back(i);
+        for (int i : left)
+            P.perm_a.push_back(i);
+        for (int j : right)
+            P.perm_b.push_back(j);
+        for (int j : common_b)
+            P.perm_b.push_back(j);
+    }
+    else {
+        for (int i : left)
+            P.perm_a.push_back(i);
+        for (int i : common_a)
+            P.perm_a.push_back(i);
+        for (int j : common_b)
+            P.perm_b.push_back(j);
+        for (int j : right)
+            P.perm_b.push_back(j);
+    }
     P.permute_a = P.permute_b = false;
     for (int i = 0; i < rank_a; i++)
         P.permute_a = P.permute_a || P.perm_a[i] != i;
@@ -892,10 +910,15 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
         P.launches++;
     }
     P.ws_gemm_off = off;
-    P.ws_gemm_bytes = GemmWorkspaceBytes(dtype, P.m, P.n, P.k);
+    P.ws_gemm_bytes = P.swap_roles ? GemmWorkspaceBytes(dtype, P.n, P.m, P.k) : GemmWorkspaceBytes(dtype, P.m, P.n, P.k);
     if (P.ws_gemm_bytes > 0)
         P.launches++; // split-K reduce, or the B expansion of the tensor-core path
     off += align(P.ws_gemm_bytes);
+    if (P.swap_roles) {
+        P.ws_ct_off = off;
+        off += align(eb * static_cast<size_t>(P.m * P.n));
+        P.launches++;
+    }
     P.ws_bytes = off;
     return 0;
 }
@@ -925,6 +948,13 @@ int LaunchContract(const ContractPlan &P, const void *a, const void *b, void *c,
         JB_TRY(LaunchPermute(P.dtype, b, w + P.ws_b_off, P.rank_b, P.extent_b.data(),
                              P.perm_b.data(), stream));
         bt = w + P.ws_b_off;
+    }
+    if (P.swap_roles) {
+        void *ct = w + P.ws_ct_off;
+        JB_TRY(LaunchGemm(P.dtype, P.n, P.m, P.k, bt, at, ct, w + P.ws_gemm_off, P.ws_gemm_bytes, stream));
+        const int64_t ext[2] = {P.n, P.m};
+        const int32_t perm[2] = {1, 0};
+        return LaunchPermute(P.dtype, ct, c, 2, ext, perm, stream);
     }
     if (P.gather_a)
         return LaunchGemmDmmaGatherA(P.m, P.n, P.k, a, P.a_free_bits.data(), static_cast<int>(P.a_free_bits.size()),

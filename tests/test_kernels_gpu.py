@@ -330,6 +330,33 @@ def test_contract_c128_gather_dmma_random_layouts(ops):
         assert rel_err(out, ref) < 1e-12, (dims, ra, nc, nf, rel_err(out, ref))
 
 
+def test_contract_c64_short_m_long_n_swaps_gemm_roles(ops):
+    """complex64 TTGT step with a short M and a long N (the m=20 shapes 64 x 2^18 x 1024, 32 x 2^18 x 256):
+    the engine computes C^T = B^T A^T on the tensor cores and transposes the small result; labels, order
+    (left ++ right) and values must be those of ContractTensors."""
+    rng = np.random.default_rng(51)
+    for ra, rb, nc in [(13, 20, 7), (13, 21, 8), (14, 22, 8)]:
+        ia = [int(v) for v in rng.permutation(ra)]
+        common = sorted(rng.choice(ia, nc, replace=False).tolist())
+        ib = common + list(range(100, 100 + rb - nc))
+        ib = [ib[i] for i in rng.permutation(rb)]
+        a = rand_c(rng, 2 ** ra, np.complex64).reshape([2] * ra)
+        b = rand_c(rng, 2 ** rb, np.complex64).reshape([2] * rb)
+        info = ops.contract_info(np.complex64, a.shape, ia, b.shape, ib)
+        assert info.kernel == 1 and info.m == 2 ** (ra - nc) and info.n == 2 ** (rb - nc)
+        out, modes = ops.contract(a, ia, b, ib)
+        want_modes, ref = jo.contract(([str(i) for i in ia], a.astype(np.complex128)), ([str(i) for i in ib], b.astype(np.complex128)))
+        assert [str(m) for m in modes] == want_modes
+        assert rel_err(out, ref) < 2e-6, (ra, rb, nc, rel_err(out, ref))
+    # integers: exact
+    a = (rng.integers(-2, 3, 2 ** 13) + 1j * rng.integers(-2, 3, 2 ** 13)).astype(np.complex64).reshape([2] * 13)
+    b = (rng.integers(-2, 3, 2 ** 20) + 1j * rng.integers(-2, 3, 2 ** 20)).astype(np.complex64).reshape([2] * 20)
+    ia, ib = list(range(13)), [0, 2, 4, 6, 8, 10, 12] + list(range(100, 113))
+    out, _ = ops.contract(a, ia, b, ib)
+    _, ref = jo.contract(([str(i) for i in ia], a.astype(np.complex128)), ([str(i) for i in ib], b.astype(np.complex128)))
+    assert np.array_equal(out, ref.astype(np.complex64))
+
+
 def test_gemm_tensor_core_exact_on_small_integers(ops):
     """Integer data: every partial product and sum is exact in FP32, so the tensor-core path must
     reproduce the integer result bit for bit (catches layout / swizzle / sign errors)."""
