@@ -9,14 +9,16 @@
 //    B' is never materialised: a lane of the B fragment needs one real number of one complex entry
 //    of the shared-memory B tile — which component, and with which sign, depends only on the lane.
 //    8*M*N*K real flops, exactly the complex product; FP64 accumulation in the MMA.
-//  * CTA tile 128 x 64 complex, K step 8 complex, 8 warps as 4 (M) x 2 (N): a warp owns 32 x 32
-//    complex = 4 x 8 m8n8 accumulator blocks (64 doubles per thread).  Per k4 step a warp issues
-//    4 + 8 shared-memory loads for 32 DMMAs; the DMMA pipe is the limit, not the LSU.
+//  * CTA tile 128 x 32 complex (template BN; 128 x 64 kept for comparison), K step 8 complex, 8 warps as
+//    4 (M) x 2 (N): a warp owns 32 x 16 complex = 4 x 4 m8n8 accumulator blocks (32 doubles per thread,
+//    118 registers: two CTAs per SM).  Per k4 step a warp issues 4 + 4 shared-memory loads for 16 DMMAs;
+//    the DMMA pipe is the limit, not the LSU.
 //  * Three-stage cp.async pipeline; shared-memory rows padded (A: 16 -> 20 doubles, B: 64 -> 66
 //    complex) so that both fragment loads are bank-conflict-free.
 //  * Ragged M and N: rows / columns beyond the matrix are zero-filled by cp.async (src-size 0) and
 //    not stored.  K must be a multiple of 8.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -27,15 +29,19 @@ namespace jb {
 namespace {
 
 constexpr int kDmBM = 128;
-constexpr int kDmBN = 64; // complex columns
+constexpr int kDmBN = 64; // complex columns of the wide tile (the narrow one is 32: two CTAs per SM)
 constexpr int kDmBK = 8;  // complex k per stage
 constexpr int kDmThreads = 256;
 constexpr int kDmStages = 3;
 constexpr int kDmAPitch = 2 * kDmBK + 4; // doubles per A' row
-constexpr int kDmBPitch = kDmBN + 2;     // complex per B row
 constexpr int kDmAStage = kDmBM * kDmAPitch;     // doubles
-constexpr int kDmBStage = kDmBK * kDmBPitch * 2; // doubles
-constexpr size_t kDmSmemBytes = sizeof(double) * kDmStages * (kDmAStage + kDmBStage);
+template <int BN> struct DmCfg {
+    static constexpr int kBPitch = BN + 2;                // complex per B row
+    static constexpr int kBStage = kDmBK * kBPitch * 2;   // doubles
+    static constexpr size_t kSmemBytes = sizeof(double) * kDmStages * (kDmAStage + kBStage);
+    static constexpr int kColBlocks = BN / 8;             // m8n8 column blocks per warp (warp = 32 x BN/2 complex)
+    static constexpr int kMinCtas = BN == 64 ? 1 : 2;
+};
 
 __device__ __forceinline__ void Dmma(double &c0, double &c1, const double a, const double b)
 {
@@ -64,19 +70,22 @@ struct DmmaGather {
     int tile_bits;
 };
 
-template <bool GATHER>
-__global__ void __launch_bounds__(kDmThreads, 1)
+template <bool GATHER, int BN>
+__global__ void __launch_bounds__(kDmThreads, DmCfg<BN>::kMinCtas)
     GemmDmmaKernel(const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C,
                    long long M, long long N, long long K, int tiles_n, int k_tiles_per_split,
                    const __grid_constant__ DmmaGather ga)
 {
+    constexpr int kDmBPitch = DmCfg<BN>::kBPitch;
+    constexpr int kDmBStage = DmCfg<BN>::kBStage;
+    constexpr int CBN = DmCfg<BN>::kColBlocks;
     extern __shared__ __align__(16) double dm_smem[];
     double *As = dm_smem;
     double *Bs = dm_smem + kDmStages * kDmAStage;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;
     const long long m0 = static_cast<long long>(blockIdx.x / tiles_n) * kDmBM;
-    const long long n0 = static_cast<long long>(blockIdx.x % tiles_n) * kDmBN;
+    const long long n0 = static_cast<long long>(blockIdx.x % tiles_n) * BN;
     // split-K: blockIdx.y owns k-tiles [kt0, kt0 + k_tiles) and writes its own partial result
     const int k_tiles_total = static_cast<int>(K / kDmBK);
     const int kt0 = blockIdx.y * k_tiles_per_split;
@@ -141,9 +150,9 @@ __global__ void __launch_bounds__(kDmThreads, 1)
             }
         }
 #pragma unroll
-        for (int i = 0; i < (kDmBK * kDmBN) / kDmThreads; i++) { // B: 512 complex, 2 per thread
+        for (int i = 0; i < (kDmBK * BN) / kDmThreads; i++) { // B: 8 x BN complex, 2 or 1 per thread
             const int q = i * kDmThreads + tid;
-            const int kr = q / kDmBN, n = q % kDmBN;
+            const int kr = q / BN, n = q % BN;
             const bool ok = n0 + n < N;
             const double2 *src = B + (ok ? (k0 + kr) * N + n0 + n : 0);
             CpAsync16(bs_s + static_cast<unsigned>(sizeof(double)) * (s * kDmBStage + (kr * kDmBPitch + n) * 2), src, ok);
@@ -151,11 +160,11 @@ __global__ void __launch_bounds__(kDmThreads, 1)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    double acc[4][8][2];
+    double acc[4][CBN][2];
 #pragma unroll
     for (int rb = 0; rb < 4; rb++)
 #pragma unroll
-        for (int cb = 0; cb < 8; cb++)
+        for (int cb = 0; cb < CBN; cb++)
             acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
 
     // lane constants of the fragments
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(kDmThreads, 1)
     const int b_comp = r ^ c;                               // 0: Re, 1: Im
     const double b_sign = (r == 1 && c == 0) ? -1.0 : 1.0;  // B'[2k+1][2n] = -Im
     const int b_k = (lane & 3) >> 1;                        // + ks * 2
-    const int b_n = wn * 32 + (lane >> 3);                  // + cb * 4
+    const int b_n = wn * (BN / 2) + (lane >> 3);            // + cb * 4
 
     for (int s = 0; s < kDmStages - 1; s++) {
         if (s < k_tiles)
@@ -185,17 +194,17 @@ __global__ void __launch_bounds__(kDmThreads, 1)
         const double *Bt = Bs + (kt % kDmStages) * kDmBStage;
 #pragma unroll
         for (int ks = 0; ks < (2 * kDmBK) / 4; ks++) {
-            double a[4], b[8];
+            double a[4], b[CBN];
 #pragma unroll
             for (int rb = 0; rb < 4; rb++)
                 a[rb] = At[(a_row + rb * 8) * kDmAPitch + ks * 4 + a_col];
 #pragma unroll
-            for (int cb = 0; cb < 8; cb++)
+            for (int cb = 0; cb < CBN; cb++)
                 b[cb] = b_sign * Bt[((ks * 2 + b_k) * kDmBPitch + b_n + cb * 4) * 2 + b_comp];
 #pragma unroll
             for (int rb = 0; rb < 4; rb++)
 #pragma unroll
-                for (int cb = 0; cb < 8; cb++)
+                for (int cb = 0; cb < CBN; cb++)
                     Dmma(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
         }
     }
@@ -208,8 +217,8 @@ __global__ void __launch_bounds__(kDmThreads, 1)
         if (m >= M)
             continue;
 #pragma unroll
-        for (int cb = 0; cb < 8; cb++) {
-            const long long n = n0 + wn * 32 + cb * 4 + (lane & 3);
+        for (int cb = 0; cb < CBN; cb++) {
+            const long long n = n0 + wn * (BN / 2) + cb * 4 + (lane & 3);
             if (n < N)
                 C[m * N + n] = double2{acc[rb][cb][0], acc[rb][cb][1]};
         }
@@ -238,13 +247,28 @@ __global__ void __launch_bounds__(256)
 
 struct DmmaShape {
     long long tiles;
-    int tiles_n, splits, k_tiles_per_split;
+    int tiles_n, splits, k_tiles_per_split, bn;
 };
+
+// 128 x 32 tiles: 118 registers -> two CTAs per SM, so one CTA's pipeline fill, barriers and epilogue overlap the
+// other's MMAs.  Measured faster than 128 x 64 (190 registers, one CTA per SM) on every shape tried: 2^21 x 64 x 64
+// 29.2 vs 25.4 TFLOP/s, 4096^3 30.8 vs 29.0, 8192 x 64 x 1024 23.6 vs 19.4.  JB_DMMA_BN=64 selects the wide tile.
+int DmmaTileN(int64_t /*m*/, int64_t /*n*/, int64_t /*k*/)
+{
+    static const int forced = [] {
+        const char *e = getenv("JB_DMMA_BN");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == 32 || forced == 64)
+        return forced;
+    return 32;
+}
 
 DmmaShape DmmaChoose(int64_t m, int64_t n, int64_t k)
 {
     DmmaShape t;
-    t.tiles_n = static_cast<int>((n + kDmBN - 1) / kDmBN);
+    t.bn = DmmaTileN(m, n, k);
+    t.tiles_n = static_cast<int>((n + t.bn - 1) / t.bn);
     t.tiles = ((m + kDmBM - 1) / kDmBM) * t.tiles_n;
     const long long k_tiles = k / kDmBK;
     const int sms = NumSMs();
@@ -330,11 +354,14 @@ int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, vo
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(GemmDmmaKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kDmSmemBytes));
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(GemmDmmaKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(kDmSmemBytes));
+        auto set = [](const void *f, size_t bytes) {
+            if (attr_err == cudaSuccess)
+                attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+        };
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 64>), DmCfg<64>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 64>), DmCfg<64>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 32>), DmCfg<32>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 32>), DmCfg<32>::kSmemBytes);
     });
     JB_CUDA(attr_err);
     const DmmaShape t = DmmaChoose(m, n, k);
@@ -346,14 +373,23 @@ int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, vo
     dim3 grid(static_cast<unsigned>(t.tiles), static_cast<unsigned>(t.splits), 1);
     DmmaGather none;
     std::memset(&none, 0, sizeof(none));
-    if (gather != nullptr)
-        GemmDmmaKernel<true><<<grid, kDmThreads, kDmSmemBytes, stream>>>(
-            static_cast<const double2 *>(a), static_cast<const double2 *>(b), dst, m, n, k, t.tiles_n,
-            t.k_tiles_per_split, *gather);
-    else
-        GemmDmmaKernel<false><<<grid, kDmThreads, kDmSmemBytes, stream>>>(
-            static_cast<const double2 *>(a), static_cast<const double2 *>(b), dst, m, n, k, t.tiles_n,
-            t.k_tiles_per_split, none);
+    const double2 *pa = static_cast<const double2 *>(a), *pb = static_cast<const double2 *>(b);
+    if (t.bn == 64) {
+        if (gather != nullptr)
+            GemmDmmaKernel<true, 64><<<grid, kDmThreads, DmCfg<64>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+                                                                                          t.k_tiles_per_split, *gather);
+        else
+            GemmDmmaKernel<false, 64><<<grid, kDmThreads, DmCfg<64>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+                                                                                           t.k_tiles_per_split, none);
+    }
+    else {
+        if (gather != nullptr)
+            GemmDmmaKernel<true, 32><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+                                                                                          t.k_tiles_per_split, *gather);
+        else
+            GemmDmmaKernel<false, 32><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+                                                                                           t.k_tiles_per_split, none);
+    }
     JB_CUDA(cudaGetLastError());
     if (t.splits > 1) {
         const long long mn = m * n;
