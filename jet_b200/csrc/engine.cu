@@ -227,7 +227,8 @@ struct jb_plan {
     std::vector<Node> nodes;
     std::vector<Step> steps;
     std::vector<int> shared_order, slice_order;
-    std::vector<Op> ops; // per-slice launch units in execution order
+    std::vector<Op> ops;        // per-slice launch units in execution order
+    std::vector<Op> shared_ops; // launch units of the slice-independent steps
     std::vector<int32_t> sliced_modes;
     std::vector<int64_t> sliced_dims;
     int64_t num_slices = 1;
@@ -267,17 +268,19 @@ namespace {
 
 int LaunchOp(jb_plan *p, const Op &op)
 {
+    // a deferred root is written unsliced (raw_offset); everything else where its consumers read it
+    const Node &out = p->nodes[op.out];
+    unsigned char *dst = p->arena + (out.is_view ? out.raw_offset : out.offset);
     if (op.kernel == 2) {
         const void *r[kChainMaxSteps];
         for (size_t i = 0; i < op.r_nodes.size(); i++)
             r[i] = p->arena + p->nodes[op.r_nodes[i]].offset;
-        return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r,
-                           p->arena + p->nodes[op.out].offset, p->arena + p->chain_stage_off, p->chain_slot,
-                           p->stream);
+        return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r, dst, p->arena + p->chain_stage_off,
+                           p->chain_slot, p->stream);
     }
     const Step &st = p->steps[op.steps[0]];
-    return LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
-                          p->arena + p->nodes[st.c].offset, p->arena + p->ws_off, p->stream);
+    return LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset, dst,
+                          p->arena + p->ws_off, p->stream);
 }
 
 int LaunchSliceViews(jb_plan *p)
@@ -324,12 +327,8 @@ int EnqueueSliceBody(jb_plan *p)
 
 int EnqueueShared(jb_plan *p)
 {
-    for (int s : p->shared_order) {
-        const Step &st = p->steps[s];
-        const Node &C = p->nodes[st.c];
-        JB_TRY(LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset,
-                              p->arena + (C.is_view ? C.raw_offset : C.offset), p->arena + p->ws_off, p->stream));
-    }
+    for (const Op &op : p->shared_ops)
+        JB_TRY(LaunchOp(p, op));
     return 0;
 }
 
@@ -339,7 +338,7 @@ int RunShared(jb_plan *p)
 {
     if (p->shared_done)
         return 0;
-    if (p->shared_order.empty()) {
+    if (p->shared_ops.empty()) {
         p->shared_done = true;
         return 0;
     }
@@ -679,10 +678,12 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             consumer[p->steps[s].a] = static_cast<int>(s);
             consumer[p->steps[s].b] = static_cast<int>(s);
         }
-        // a step can join a chain whose running tensor is node x when its other operand is small
+        // a step can join a chain whose running tensor is node x when its other operand is small; chains
+        // never mix slice-independent and per-slice steps
+        bool want_shared = false;
         auto as_operand = [&](int s, int x, ChainOperand *o, int *r_node) {
             const Step &st = p->steps[s];
-            if (st.shared || st.cp.kernel != 0)
+            if (st.shared != want_shared || st.cp.kernel != 0)
                 return false;
             const bool x_left = st.a == x;
             const int r = x_left ? st.b : st.a;
@@ -696,9 +697,11 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             return true;
         };
         std::vector<char> taken(p->steps.size(), 0);
-        std::vector<Op> ops;
         const int max_tile = ChainMaxTileBits(p->dtype);
-        for (int s : p->slice_order) {
+        auto build = [&](const std::vector<int> &order, bool shared_steps) {
+        want_shared = shared_steps;
+        std::vector<Op> ops;
+        for (int s : order) {
             if (taken[s])
                 continue;
             const Step &st = p->steps[s];
@@ -748,7 +751,10 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         // a unit runs where its LAST step stood in the path: everything it reads exists by then
         std::stable_sort(ops.begin(), ops.end(),
                          [](const Op &x, const Op &y) { return x.steps.back() < y.steps.back(); });
-        p->ops = ops;
+        return ops;
+        };
+        p->ops = build(p->slice_order, false);
+        p->shared_ops = build(p->shared_order, true); // the slice-independent steps fuse the same way
         for (size_t o = 0; o < p->ops.size(); o++)
             for (int cs : p->ops[o].steps)
                 p->steps[cs].op = static_cast<int>(o);
@@ -761,11 +767,9 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         bool shared;
     };
     std::vector<Exec> exec;
-    for (int s : p->shared_order)
-        exec.push_back({{p->steps[s].a, p->steps[s].b}, p->steps[s].c, true});
-    for (const Op &op : p->ops) {
+    auto add_exec = [&](const Op &op, bool shared) {
         Exec e;
-        e.shared = false;
+        e.shared = shared;
         e.out = op.out;
         if (op.kernel == 2) {
             e.reads = op.r_nodes;
@@ -775,7 +779,11 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             e.reads = {p->steps[op.steps[0]].a, p->steps[op.steps[0]].b};
         }
         exec.push_back(e);
-    }
+    };
+    for (const Op &op : p->shared_ops)
+        add_exec(op, true);
+    for (const Op &op : p->ops)
+        add_exec(op, false);
     for (size_t e = 0; e < exec.size(); e++) {
         for (int in : exec[e].reads) {
             p->nodes[in].last_use = static_cast<int>(e);
