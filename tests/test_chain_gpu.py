@@ -122,6 +122,9 @@ def test_m10_fused_equals_unfused_and_reference(data_dir, dt):
     with ContractionPlan(net, sliced, fuse=True, store_results=True) as fused, \
             ContractionPlan(net, sliced, fuse=False, store_results=True) as plain:
         assert fused.stats.chains > 0 and plain.stats.chains == 0
+        # deferred slicing: small subtrees with open sliced indices moved to the slice-independent phase
+        assert fused.stats.steps_shared > plain.stats.steps_shared
+        assert fused.stats.jet_flops_per_slice == plain.stats.jet_flops_per_slice  # Jet-convention flops unchanged
         assert fused.stats.launches_per_slice < plain.stats.launches_per_slice
         assert fused.stats.fused_bytes_per_slice < 0.6 * fused.stats.bytes_per_slice
         ids = [0, 1, 17, 63]
