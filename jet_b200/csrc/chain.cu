@@ -450,7 +450,7 @@ template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, in
 {
     using C = typename Cplx<R>::type;
     const int ct = ChainCfg<R>::kGroupThreads;
-    size_t b = sizeof(C) * kChainBuffers * (size_t(1) << log_tile);
+    size_t b = sizeof(C) * ((kChainBuffers * (size_t(1) << log_tile) + 1) & ~size_t(1));
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
     b += sizeof(ChainMemEntry) * 2 * kChainMemTabLen;           // load / store tables
     b += sizeof(uint16_t) * static_cast<size_t>(n_stages) * ct; // per-thread stage offsets
@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
     extern __shared__ __align__(16) unsigned char chain_smem[];
     C *tiles = reinterpret_cast<C *>(chain_smem);
     const int tile_elems = 1 << p.log_tile;
-    C *Bm = tiles + kChainBuffers * tile_elems;
+    // (16-byte aligned also when the tile is a single complex64 element: the matrices are read with float4 loads)
+    C *Bm = tiles + ((kChainBuffers * tile_elems + 1) & ~1);
     ChainMemEntry *tab_in = reinterpret_cast<ChainMemEntry *>(Bm + ((p.resident_elems + 1) & ~1));
     ChainMemEntry *tab_out = tab_in + kChainMemTabLen;
     uint16_t *atid = reinterpret_cast<uint16_t *>(tab_out + kChainMemTabLen);

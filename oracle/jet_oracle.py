@@ -68,6 +68,10 @@ def contract(a: Tensor, b: Tensor) -> Tensor:
     """
     ia, A = a
     ib, B = b
+    # a scalar tensor (no indices, one element: Tensor.hpp:47, and what SliceIndex leaves of a rank-1 tensor)
+    # may arrive with shape (1,); give every operand exactly one axis per index
+    A = np.reshape(A, np.shape(A)[len(np.shape(A)) - len(ia):] if len(ia) else ())
+    B = np.reshape(B, np.shape(B)[len(np.shape(B)) - len(ib):] if len(ib) else ())
     left, right, common = contraction_indices(ia, ib)
     dim_a = dict(zip(ia, A.shape))
     dim_b = dict(zip(ib, B.shape))

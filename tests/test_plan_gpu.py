@@ -188,3 +188,26 @@ def test_lane_plans_match_single_plan(data_dir):
         assert abs(a - b) / abs(a) < 1e-12
         b2 = lanes.amplitude(ids).reshape(-1)[0]
         assert b2 == b  # deterministic for a fixed lane count
+
+
+def test_fully_sliced_leaf_scalar_chain():
+    """Regression (found by tools/stress_plan_gpu.py): when every index of a leaf is sliced, the chained
+    tensor of a fused run is a scalar and the chain's shared-memory tile holds ONE element; the step matrices
+    behind it must stay 16-byte aligned."""
+    from jet_b200 import ContractionPlan, LanePlans, NetworkFile
+    rng = np.random.default_rng(174)
+
+    def rc(shape):
+        n = int(np.prod(shape))
+        return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64).reshape(shape)
+
+    tensors = [(["e0", "e3", "e4"], rc([2, 2, 2])), (["e1", "e0"], rc([2, 2])), (["e1", "e4", "e3", "e2"], rc([2] * 4)),
+               (["e2"], rc([2]))]
+    path = [(3, 2), (0, 4), (5, 1)]
+    sliced = ["e3", "e1", "e0", "e4"]
+    ref = np.asarray(jo.amplitude(jo.Network(tensors, path), sliced)).reshape(-1)[0]
+    for make in (lambda: ContractionPlan(NetworkFile(tensors, path), sliced),
+                 lambda: LanePlans(NetworkFile(tensors, path), sliced, lanes=2)):
+        with make() as plan:
+            got = plan.amplitude().reshape(-1)[0]
+            assert rel(got, ref) < 1e-5
