@@ -1,7 +1,7 @@
 """Random tensor networks (random graph, random path, random sliced indices, optional open indices) through
 jb_plan_* on the GPU against the numpy oracle — exercises deferred slicing, fused chains of shared and per-slice
 steps, slice views and the FP64 accumulation on shapes no fixture covers.
-  python tools/stress_plan_gpu.py [trials]"""
+  python tools/stress_plan_gpu.py [trials] [only_trial | -1] [seed]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +11,8 @@ from oracle import jet_oracle as jo  # noqa: E402  (checker)
 
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 only = int(sys.argv[2]) if len(sys.argv) > 2 else -1  # run just this trial (same random sequence), verbosely
-rng = np.random.default_rng(31337)
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 31337
+rng = np.random.default_rng(seed)
 bad = ran = 0
 for trial in range(trials):
     dtype = np.complex64 if rng.integers(0, 2) else np.complex128
