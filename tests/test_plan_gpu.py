@@ -211,3 +211,24 @@ def test_fully_sliced_leaf_scalar_chain():
         with make() as plan:
             got = plan.amplitude().reshape(-1)[0]
             assert rel(got, ref) < 1e-5
+
+
+def test_gbs_fock8_c128_matches_reference_golden(data_dir):
+    """The compute-bound complex128 workload (dim-8 indices, 2^27-element intermediates: DMMA GEMMs with gathered
+    A, split-K, deferred slicing) against the reference's complex128 amplitude of the same file
+    (tools/make_fock8_golden.py), all 64 slices of the two greedily chosen indices."""
+    gpath = os.path.join(os.path.dirname(__file__), "golden", "amplitudes_fock8.json")
+    if not os.path.exists(gpath):
+        pytest.skip("fock8 golden not generated")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from jet_b200 import ContractionPlan
+    g = json.load(open(gpath))["gbs_fock8_total0_complex128"]
+    want = complex(g["re"], g["im"])
+    net, sliced, dt, _ = bench.load_network("gbs_fock8_total0_s2")
+    assert dt == "complex128"
+    with ContractionPlan(net, sliced) as plan:
+        assert plan.num_slices == 64
+        got = complex(plan.amplitude().reshape(-1)[0])
+    assert abs(got - want) / abs(want) < 1e-12, (got, want)
