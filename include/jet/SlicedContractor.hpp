@@ -4,10 +4,14 @@
 // hand the UNSLICED network, the path and the list of sliced indices to one device-resident plan
 // (jb_plan_*, include/jetb200.h).  Slices are selected on the device, slice-independent steps run
 // once, the per-slice steps replay as a CUDA graph, and the sum over slices is accumulated on the
-// device in double precision.  This class is an addition to the Jet API (the reference has no
-// equivalent); TaskBasedContractor keeps the reference's interface.
+// device in double precision.  `lanes` > 1 keeps that many slices in flight (one plan — arena, stream,
+// CUDA graph — per lane; pays off when one slice cannot fill the GPU), the stream analogue of the
+// reference running tasks of different slices on Taskflow workers (TaskBasedContractor.hpp:322).
+// This class is an addition to the Jet API (the reference has no equivalent); TaskBasedContractor
+// keeps the reference's interface.
 #pragma once
 
+#include <algorithm>
 #include <complex>
 #include <cstdint>
 #include <string>
@@ -27,8 +31,9 @@ template <class TensorType> class SlicedContractor {
     using scalar_t = typename TensorType::scalar_type_t;
 
     SlicedContractor(const TensorNetwork<TensorType> &tn, const PathInfo::Path &path,
-                     const std::vector<std::string> &sliced_indices, int device = 0, int flags = 0)
+                     const std::vector<std::string> &sliced_indices, int device = 0, int flags = 0, int lanes = 1)
     {
+        JET_ABORT_IF(lanes < 1 || lanes > 5, "SlicedContractor: lanes must be in 1..5.");
         std::unordered_map<std::string, int32_t> label;
         std::vector<int32_t> rank, mode, flat_path, sliced;
         std::vector<int64_t> extent;
@@ -67,12 +72,20 @@ template <class TensorType> class SlicedContractor {
         d.num_sliced = static_cast<int32_t>(sliced.size());
         d.sliced_modes = sliced.data();
         d.flags = flags;
-        JET_JB_CHECK(jb_plan_create(&d, &plan_));
-        JET_JB_CHECK(jb_plan_stats(plan_, &stats_));
+        for (int l = 0; l < lanes; l++) {
+            jb_plan *plan = nullptr;
+            JET_JB_CHECK(jb_plan_create(&d, &plan));
+            plans_.push_back(plan);
+        }
+        JET_JB_CHECK(jb_plan_stats(plans_[0], &stats_));
     }
     SlicedContractor(const SlicedContractor &) = delete;
     SlicedContractor &operator=(const SlicedContractor &) = delete;
-    ~SlicedContractor() { jb_plan_destroy(plan_); }
+    ~SlicedContractor()
+    {
+        for (jb_plan *plan : plans_)
+            jb_plan_destroy(plan);
+    }
 
     size_t NumSlices() const noexcept { return static_cast<size_t>(stats_.num_slices); }
     double GetFlops() const noexcept { return stats_.jet_flops_per_slice; } // PathInfo convention
@@ -83,10 +96,20 @@ template <class TensorType> class SlicedContractor {
     {
         if (count == static_cast<size_t>(-1))
             count = NumSlices() - first;
-        JET_JB_CHECK(jb_plan_reset(plan_));
-        JET_JB_CHECK(jb_plan_run(plan_, static_cast<int64_t>(first), static_cast<int64_t>(count)));
-        std::vector<double> acc(2 * static_cast<size_t>(stats_.result_elems));
-        JET_JB_CHECK(jb_plan_result(plan_, acc.data()));
+        // lane l takes the l-th contiguous block of the range; all lanes are enqueued before any is read back
+        const size_t lanes = plans_.size(), block = (count + lanes - 1) / lanes;
+        for (size_t l = 0; l < lanes; l++) {
+            const size_t lo = std::min(count, l * block), hi = std::min(count, (l + 1) * block);
+            JET_JB_CHECK(jb_plan_reset(plans_[l]));
+            if (hi > lo)
+                JET_JB_CHECK(jb_plan_run(plans_[l], static_cast<int64_t>(first + lo), static_cast<int64_t>(hi - lo)));
+        }
+        std::vector<double> acc(2 * static_cast<size_t>(stats_.result_elems), 0.0), part(acc.size());
+        for (size_t l = 0; l < lanes; l++) { // summed in lane order: deterministic for a given lane count
+            JET_JB_CHECK(jb_plan_result(plans_[l], part.data()));
+            for (size_t i = 0; i < acc.size(); i++)
+                acc[i] += part[i];
+        }
         std::vector<std::string> indices;
         std::vector<size_t> shape;
         for (int i = 0; i < stats_.result_rank; i++) {
@@ -104,12 +127,16 @@ template <class TensorType> class SlicedContractor {
     float LastMilliseconds()
     {
         float ms = 0;
-        JET_JB_CHECK(jb_plan_last_ms(plan_, &ms));
+        for (jb_plan *plan : plans_) { // the lanes run concurrently: the longest one
+            float m = 0;
+            JET_JB_CHECK(jb_plan_last_ms(plan, &m));
+            ms = std::max(ms, m);
+        }
         return ms;
     }
 
   private:
-    jb_plan *plan_ = nullptr;
+    std::vector<jb_plan *> plans_;
     jb_plan_stats_t stats_{};
     std::vector<std::string> names_;
 };

@@ -195,8 +195,9 @@ template <class T> void BindContractors(py::module_ &m, const char *tbc_name, co
     using SC = Jet::SlicedContractor<tensor_t>;
     py::class_<SC>(m, sliced_name, "Device-resident sliced contraction (B200 extension).")
         .def(py::init<const Jet::TensorNetwork<tensor_t> &, const Jet::PathInfo::Path &,
-                      const std::vector<std::string> &, int, int>(),
-             py::arg("tn"), py::arg("path"), py::arg("sliced_indices"), py::arg("device") = 0, py::arg("flags") = 0)
+                      const std::vector<std::string> &, int, int, int>(),
+             py::arg("tn"), py::arg("path"), py::arg("sliced_indices"), py::arg("device") = 0, py::arg("flags") = 0,
+             py::arg("lanes") = 1)
         .def_property_readonly("num_slices", &SC::NumSlices)
         .def_property_readonly("flops", &SC::GetFlops)
         .def("contract", [](SC &sc, size_t first, py::object count) {

@@ -481,6 +481,12 @@ void TestSlicedFile(const std::string &file_name)
     CHECK(std::abs(std::complex<double>(via_tbc) - want) / std::abs(want) < 1e-5);
     CHECK(std::abs(std::complex<double>(via_plan) - want) / std::abs(want) < 1e-5);
     std::cout << "m10 slices 0..3: tbc " << via_tbc << " plan " << via_plan << " want " << want << std::endl;
+    // three slices in flight: same sum (FP64 accumulators per lane, added in lane order)
+    SlicedContractor<tensor_t> sc3(file.tensors, path, sliced, 0, 0, 3);
+    const c64 via_lanes = sc3.Contract(0, 4).GetScalar();
+    CHECK(std::abs(std::complex<double>(via_lanes) - want) / std::abs(want) < 1e-5);
+    CHECK(std::abs(std::complex<double>(sc3.Contract().GetScalar()) - std::complex<double>(sc.Contract().GetScalar())) <
+          1e-6 * std::abs(std::complex<double>(sc.Contract().GetScalar())));
 }
 
 int main(int argc, char **argv)
