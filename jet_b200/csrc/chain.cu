@@ -401,14 +401,18 @@ __device__ __forceinline__ void ChainRegisterStage(unsigned char *__restrict__ t
 // are tabulated in shared memory once per CTA.
 // Hand-off is by named barriers (bar.arrive by the producer, bar.sync by the consumer): full[b]
 // load -> compute, done[b] compute -> store, free[b] store -> load.
-constexpr int kChainBuffers = 3;
+// Two shapes of the CTA (template parameters NG = compute groups, NB = tile buffers):
+//   NG 2, NB 3: tiles of up to 2^13 complex64 (64 KB each) — the longest chains;
+//   NG 3, NB 5: tiles of up to 2^12 elements — three tiles in the FMA pipe at once (JB_CHAIN_GROUPS=3).
+// complex128 always runs one group over three buffers.
 constexpr int kChainLoadThreads = 64;
 constexpr int kChainStoreThreads = 64;
 constexpr int kChainMemThreads = kChainLoadThreads + kChainStoreThreads;
 constexpr int kChainMemTabLen = 1 << (kChainMaxTileBits - kChainMemLogLanes);
 static_assert(kChainLoadThreads == (1 << kChainMemLogLanes) && kChainStoreThreads == (1 << kChainMemLogLanes),
               "memory warps: one thread per lane of the tile walk");
-constexpr int kBarFull = 2, kBarDone = 5, kBarFree = 8, kBarCompute = 11; // kBarCompute + group
+// named barriers: full[b] = 1 + b, done[b] = 1 + NB + b, stage barrier of group g = 1 + 2 NB + g (<= 15 in all);
+// "buffer b is free again" (store -> load) is a counter in shared memory, polled by the load warps
 
 struct __align__(16) ChainMemEntry {
     unsigned long long g; // byte offset in X_0 / X_k
@@ -421,11 +425,9 @@ template <typename R> struct ChainCfg {
     // complex64 runs two groups on two different tiles, so that one group's FMA phases overlap the
     // other's shared-memory phases and barriers; complex128 has the registers for one group only.
     static constexpr int kLogThreads = 8;
-    static constexpr int kGroups = sizeof(R) == 4 ? 2 : 1;
     static constexpr int kGroupThreads = 1 << kLogThreads;
-    static constexpr int kComputeThreads = kGroups * kGroupThreads;
-    static constexpr int kCtaThreads = kComputeThreads + kChainMemThreads;
 };
+__host__ __device__ constexpr int ChainCtaThreads(int groups) { return groups * 256 + kChainMemThreads; }
 static_assert(ChainCfg<float>::kLogThreads == ChainLogThreads(8) && ChainCfg<double>::kLogThreads == ChainLogThreads(16),
               "planner and kernel must agree on the compute thread count");
 
@@ -446,19 +448,20 @@ __device__ __forceinline__ void BarArrive(int id, int count)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, int n_stages)
+template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, int n_stages, int buffers)
 {
     using C = typename Cplx<R>::type;
     const int ct = ChainCfg<R>::kGroupThreads;
-    size_t b = sizeof(C) * ((kChainBuffers * (size_t(1) << log_tile) + 1) & ~size_t(1));
+    size_t b = sizeof(C) * ((static_cast<size_t>(buffers) * (size_t(1) << log_tile) + 1) & ~size_t(1));
+    b += 64; // free counters
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
     b += sizeof(ChainMemEntry) * 2 * kChainMemTabLen;           // load / store tables
     b += sizeof(uint16_t) * static_cast<size_t>(n_stages) * ct; // per-thread stage offsets
     return b;
 }
 
-template <typename R>
-__global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
+template <typename R, int NG, int NB>
+__global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
                 typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
                 const __grid_constant__ ChainPtrs rp)
@@ -466,8 +469,10 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
     using C = typename Cplx<R>::type;
     constexpr int LOGT = ChainCfg<R>::kLogThreads;
     constexpr int GT = 1 << LOGT;                      // threads of one compute group
-    constexpr int NG = ChainCfg<R>::kGroups;           // compute groups (tiles in flight in the FMA pipe)
-    constexpr int CT = ChainCfg<R>::kComputeThreads;   // all compute threads
+    constexpr int CT = NG * GT;                        // all compute threads (NG groups, NB tile buffers)
+    constexpr int kChainBuffers = NB;
+    constexpr int kBarFull = 1, kBarDone = 1 + NB, kBarCompute = 1 + 2 * NB;
+    static_assert(kBarCompute + NG <= 16, "named barriers");
     constexpr int ML = kChainMemLogLanes;
     // complex64: a store thread owns two X_k-adjacent elements (store-index bit 0) -> 16-byte stores
     constexpr int PAIR = sizeof(C) == 8 ? 1 : 0;
@@ -475,7 +480,8 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
     C *tiles = reinterpret_cast<C *>(chain_smem);
     const int tile_elems = 1 << p.log_tile;
     // (16-byte aligned also when the tile is a single complex64 element: the matrices are read with float4 loads)
-    C *Bm = tiles + ((kChainBuffers * tile_elems + 1) & ~1);
+    int *free_cnt = reinterpret_cast<int *>(tiles + ((kChainBuffers * tile_elems + 1) & ~1)); // [NB], 64 bytes
+    C *Bm = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(free_cnt) + 64);
     ChainMemEntry *tab_in = reinterpret_cast<ChainMemEntry *>(Bm + ((p.resident_elems + 1) & ~1));
     ChainMemEntry *tab_out = tab_in + kChainMemTabLen;
     uint16_t *atid = reinterpret_cast<uint16_t *>(tab_out + kChainMemTabLen);
@@ -512,6 +518,8 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
         }
     }
 
+    if (tid < 16)
+        free_cnt[tid] = 0;
     // resident operands -> shared memory as K x np matrices (columns n >= N are zero): the matrices
     // of the steps that run through the generic shared-memory path
     for (int s = 0; s < p.n_steps; s++) {
@@ -520,7 +528,7 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
         const int np = q.np;
         const int N = 1 << q.log_n;
         const int total = np << q.log_k;
-        for (int e = tid; e < total; e += ChainCfg<R>::kCtaThreads) {
+        for (int e = tid; e < total; e += ChainCtaThreads(NG)) {
             const unsigned k = e / np, n = e % np;
             C v = C{R(0), R(0)};
             if (static_cast<int>(n) < N)
@@ -533,7 +541,6 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
     const int n_my = static_cast<int>((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles of this CTA
     constexpr int kFullCount = kChainLoadThreads + GT;
     constexpr int kDoneCount = GT + kChainStoreThreads;
-    constexpr int kFreeCount = kChainStoreThreads + kChainLoadThreads;
     const unsigned tiles_s = static_cast<unsigned>(__cvta_generic_to_shared(tiles));
     const unsigned tile_bytes = static_cast<unsigned>(tile_elems * sizeof(C));
 
@@ -606,8 +613,13 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
             const int b = i % kChainBuffers;
             const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(i) * gridDim.x;
             const unsigned long long base = Deposit(t, p.outer_in, p.log_outer) * sizeof(C);
-            if (i >= kChainBuffers)
-                BarSync(kBarFree + b, kFreeCount);
+            if (i >= kChainBuffers) {
+                // buffer b has been written out (i / NB) times by both store warps
+                const int want = 2 * (i / kChainBuffers);
+                while (*reinterpret_cast<volatile int *>(free_cnt + b) < want)
+                    __nanosleep(64);
+                __threadfence_block();
+            }
             const unsigned buf_s = tiles_s + static_cast<unsigned>(b) * tile_bytes;
             const unsigned char *src = reinterpret_cast<const unsigned char *>(X0) + (base + g_lane);
             if (ok) {
@@ -672,8 +684,11 @@ __global__ void __launch_bounds__(ChainCfg<R>::kCtaThreads, 1)
                     }
                 }
             }
-            if (i + kChainBuffers < n_my)
-                BarArrive(kBarFree + b, kFreeCount);
+            // every global store of this thread has read its shared-memory source; one release per warp
+            __threadfence_block();
+            __syncwarp();
+            if ((lt & 31) == 0)
+                atomicAdd(free_cnt + b, 1);
         }
     }
 }
@@ -711,6 +726,16 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// complex64 tiles of up to 2^12 elements fit five buffers: three compute groups (experiment: JB_CHAIN_GROUPS=3)
+bool ChainUseThreeGroups(bool is_c64, int log_tile)
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_CHAIN_GROUPS");
+        return e && e[0] == '3';
+    }();
+    return enabled && is_c64 && log_tile <= 12;
+}
+
 template <typename R>
 int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk, void *staging, int slot,
                  cudaStream_t stream)
@@ -733,15 +758,26 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         JB_CUDA(cudaGetLastError());
     }
     (void)staging;
-    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages);
+    const bool wide = ChainUseThreeGroups(sizeof(C) == 8, p.log_tile);
+    const int buffers = wide ? 5 : 3;
+    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
-    auto kernel = ChainKernel<R>;
-    if (smem > 48 * 1024)
-        JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(p.n_tiles, NumSMs())));
-    kernel<<<grid, ChainCfg<R>::kCtaThreads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p,
-                                                     ptrs);
+    auto launch = [&](auto kernel, int threads) -> int {
+        if (smem > 48 * 1024)
+            JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<grid, threads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p, ptrs);
+        return 0;
+    };
+    if constexpr (sizeof(C) == 8) {
+        if (wide)
+            JB_TRY(launch(ChainKernel<R, 3, 5>, ChainCtaThreads(3)));
+        else
+            JB_TRY(launch(ChainKernel<R, 2, 3>, ChainCtaThreads(2)));
+    }
+    else {
+        JB_TRY(launch(ChainKernel<R, 1, 3>, ChainCtaThreads(1)));
+    }
     JB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -897,8 +933,9 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     {
         const size_t smem =
             spec.elem_bytes == 8
-                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages)
-                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages);
+                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages,
+                                        ChainUseThreeGroups(true, lay.params.log_tile) ? 5 : 3)
+                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, 3);
         if (smem > 227 * 1024) {
             *why = "shared memory";
             return 1;
