@@ -390,17 +390,19 @@ __device__ __forceinline__ void ChainRegisterStage(unsigned char *__restrict__ t
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-// One persistent CTA per SM, warp-specialised over a ring of three tile buffers:
-//   compute warps (16 for complex64, 8 for complex128): apply the chain to tile i in place, stage by
-//               stage (FMA pipe only — these warps never touch global memory).  Four compute warps per
-//               scheduler keep the FMA pipe fed while others are between phases;
+// One persistent CTA per SM, warp-specialised over a ring of tile buffers:
+//   compute warps: groups of 8 warps, each group applying the chain to ITS tile in place, stage by stage
+//               (FMA pipe only — these warps never touch global memory).  complex64 runs two groups on
+//               two different tiles, so one group's FMA phases overlap the other's shared-memory phases
+//               and stage barriers; complex128 one group;
 //   2 load warps:  cp.async tile i+1 / i+2 from X_0 into a free buffer;
 //   2 store warps: write tile i-1 from its buffer to X_k, two adjacent complex64 per 16-byte store.
 // One memory warp sits on each of the four schedulers.  Their per-element address work is one XOR
 // (shared-memory side) and one 64-bit add (global side): the thread-independent halves of both maps
 // are tabulated in shared memory once per CTA.
-// Hand-off is by named barriers (bar.arrive by the producer, bar.sync by the consumer): full[b]
-// load -> compute, done[b] compute -> store, free[b] store -> load.
+// Hand-off: named barriers (bar.arrive by the producer, bar.sync by the consumer) full[b] load ->
+// compute and done[b] compute -> store; store -> load ("buffer b is free again") is a counter in shared
+// memory that the load warps poll.
 // Two shapes of the CTA (template parameters NG = compute groups, NB = tile buffers):
 //   NG 2, NB 3: tiles of up to 2^13 complex64 (64 KB each) — the longest chains;
 //   NG 3, NB 5: tiles of up to 2^12 elements — three tiles in the FMA pipe at once (JB_CHAIN_GROUPS=3).
