@@ -312,7 +312,6 @@ namespace {
 // Operator-level chains share one constant-bank slot per device: calls are serialised with a mutex
 // and, across streams, with an event recorded after each launch.
 struct OperatorChainState {
-    void *staging = nullptr;
     cudaEvent_t done = nullptr;
 };
 std::mutex g_op_chain_mutex;
@@ -326,14 +325,13 @@ int LaunchOperatorChain(const ChainOp &op, const void *d_x, const void *const *d
     JB_REQUIRE(dev >= 0 && dev < 64, "chain: device index out of range");
     std::lock_guard<std::mutex> lock(g_op_chain_mutex);
     OperatorChainState &st = g_op_chain[dev];
-    if (st.staging == nullptr) {
-        JB_CUDA(cudaMalloc(&st.staging, ChainStagingBytes()));
+    if (st.done == nullptr) {
         JB_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     }
     else {
         JB_CUDA(cudaStreamWaitEvent(stream, st.done, 0)); // the previous call may be on another stream
     }
-    JB_TRY(LaunchChain(op, d_x, d_r, d_out, st.staging, ChainOperatorSlot(), stream));
+    JB_TRY(LaunchChain(op, d_x, d_r, d_out, ChainOperatorSlot(), stream));
     JB_CUDA(cudaEventRecord(st.done, stream));
     return 0;
 }

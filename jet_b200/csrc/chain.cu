@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     }
 }
 
-// Small operands -> staging buffer, as K x np matrices in the form the register stages read from the
+// Small operands -> this launch's constant-bank slot, as K x np matrices in the form the register stages read from the
 // constant bank: complex64 (b.x, b.y, -b.y, b.x), complex128 (b.x, b.y); columns n >= N are zero.
 template <typename R>
 __global__ void __launch_bounds__(256)
@@ -739,11 +739,11 @@ bool ChainUseThreeGroups(bool is_c64, int log_tile)
 }
 
 template <typename R>
-int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk, void *staging, int slot,
+int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk, int slot,
                  cudaStream_t stream)
 {
     using C = typename Cplx<R>::type;
-    JB_REQUIRE(slot >= 0 && slot < kChainConstSlots && staging != nullptr, "chain: no constant-bank slot");
+    JB_REQUIRE(slot >= 0 && slot < kChainConstSlots, "chain: no constant-bank slot");
     p.const_base = slot * kChainConstEntries;
     // The matrices of the register stages go straight into this launch's constant-bank slot: the
     // bank is ordinary device memory behind the symbol's address, and a kernel boundary separates
@@ -759,7 +759,6 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
         JB_CUDA(cudaGetLastError());
     }
-    (void)staging;
     const bool wide = ChainUseThreeGroups(sizeof(C) == 8, p.log_tile);
     const int buffers = wide ? 5 : 3;
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers);
@@ -975,7 +974,6 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     return 0;
 }
 
-size_t ChainStagingBytes() { return sizeof(uint4) * kChainConstEntries; }
 
 // constant-bank slots: [0, kChainConstSlots - 1) for plans, the last one for operator-level calls
 namespace {
@@ -1005,7 +1003,7 @@ void ChainReleaseSlot(int device, int slot)
 
 int ChainOperatorSlot() { return kChainConstSlots - 1; }
 
-int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, void *staging, int slot,
+int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, int slot,
                 cudaStream_t stream)
 {
     ChainParams p;
@@ -1016,8 +1014,8 @@ int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *x
     for (int s = 0; s < op.n_steps; s++)
         ptrs.r[s] = r[s];
     if (op.dtype == JB_C64)
-        return LaunchChainT<float>(p, ptrs, x0, xk, staging, slot, stream);
-    return LaunchChainT<double>(p, ptrs, x0, xk, staging, slot, stream);
+        return LaunchChainT<float>(p, ptrs, x0, xk, slot, stream);
+    return LaunchChainT<double>(p, ptrs, x0, xk, slot, stream);
 }
 
 } // namespace jb

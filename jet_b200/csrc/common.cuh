@@ -158,14 +158,13 @@ bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left);
 int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vector<int64_t> &extent_x,
                 const std::vector<ChainOperand> &ops, int max_tile_bits, ChainOp *out,
                 std::string *why);
-// The step matrices of a chain are staged through a device buffer of ChainStagingBytes() and one
-// constant-bank slot: plans acquire a slot for their lifetime (-1: none free -> no fusion), the
-// operator-level entry points share ChainOperatorSlot().
-size_t ChainStagingBytes();
+// The step matrices of a chain's register stages live in a constant-bank slot (a gather kernel writes
+// them there before the chain kernel): plans acquire a slot for their lifetime (-1: none free -> no
+// fusion), the operator-level entry points share ChainOperatorSlot().
 int ChainAcquireSlot(int device);
 void ChainReleaseSlot(int device, int slot);
 int ChainOperatorSlot();
-int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, void *staging, int slot,
+int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, int slot,
                 cudaStream_t stream);
 
 // ---- elementwise ---------------------------------------------------------------------------------

@@ -237,7 +237,7 @@ struct jb_plan {
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0;
     size_t ws_off = 0, ws_bytes = 0;
-    size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0, chain_stage_off = 0;
+    size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0;
     int chain_slot = -1; // constant-bank slot of the fused chains (-1: none, fusion off)
     int64_t store_cap = 0, list_cap = 0;
     int64_t result_elems = 1;
@@ -275,8 +275,7 @@ int LaunchOp(jb_plan *p, const Op &op)
         const void *r[kChainMaxSteps];
         for (size_t i = 0; i < op.r_nodes.size(); i++)
             r[i] = p->arena + p->nodes[op.r_nodes[i]].offset;
-        return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r, dst, p->arena + p->chain_stage_off,
-                           p->chain_slot, p->stream);
+        return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r, dst, p->chain_slot, p->stream);
     }
     const Step &st = p->steps[op.steps[0]];
     return LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset, dst,
@@ -808,7 +807,6 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     p->list_cap = std::max<int64_t>(std::min<int64_t>(p->num_slices, kMaxListed), 1);
     p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
     p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
-    p->chain_stage_off = alloc.Alloc(ChainStagingBytes());
     for (size_t e = 0; e < exec.size(); e++) {
         Node &C = p->nodes[exec[e].out];
         if (C.is_view) { // the view buffer exists already; the unsliced tensor lives for the whole run
