@@ -39,7 +39,6 @@ template <int BN> struct DmCfg {
     static constexpr int kBPitch = BN + 2;                // complex per B row
     static constexpr int kBStage = kDmBK * kBPitch * 2;   // doubles
     static constexpr size_t kSmemBytes = sizeof(double) * kDmStages * (kDmAStage + kBStage);
-    static constexpr int kColBlocks = BN / 8;             // m8n8 column blocks per warp (warp = 32 x BN/2 complex)
     static constexpr int kMinCtas = BN == 64 ? 1 : 2;
 };
 
@@ -70,7 +69,9 @@ struct DmmaGather {
     int tile_bits;
 };
 
-template <bool GATHER, int BN>
+// WM = warps along M: 4 (a warp owns 32 rows x BN/2 columns) or, for M <= 64, 2 (32 rows x BN/4 columns:
+// no warp works on rows that do not exist)
+template <bool GATHER, int BN, int WM>
 __global__ void __launch_bounds__(kDmThreads, DmCfg<BN>::kMinCtas)
     GemmDmmaKernel(const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C,
                    long long M, long long N, long long K, int tiles_n, int k_tiles_per_split,
@@ -78,12 +79,15 @@ __global__ void __launch_bounds__(kDmThreads, DmCfg<BN>::kMinCtas)
 {
     constexpr int kDmBPitch = DmCfg<BN>::kBPitch;
     constexpr int kDmBStage = DmCfg<BN>::kBStage;
-    constexpr int CBN = DmCfg<BN>::kColBlocks;
+    constexpr int WN = 8 / WM;             // warps along N
+    constexpr int WTN = BN / WN;           // complex columns per warp
+    constexpr int CBN = WTN / 4;           // m8n8 column blocks per warp
+    static_assert(WM * WN == 8 && CBN >= 1, "warp layout");
     extern __shared__ __align__(16) double dm_smem[];
     double *As = dm_smem;
     double *Bs = dm_smem + kDmStages * kDmAStage;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp / WN, wn = warp % WN;
     const long long m0 = static_cast<long long>(blockIdx.x / tiles_n) * kDmBM;
     const long long n0 = static_cast<long long>(blockIdx.x % tiles_n) * BN;
     // split-K: blockIdx.y owns k-tiles [kt0, kt0 + k_tiles) and writes its own partial result
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(kDmThreads, DmCfg<BN>::kMinCtas)
     const int b_comp = r ^ c;                               // 0: Re, 1: Im
     const double b_sign = (r == 1 && c == 0) ? -1.0 : 1.0;  // B'[2k+1][2n] = -Im
     const int b_k = (lane & 3) >> 1;                        // + ks * 2
-    const int b_n = wn * (BN / 2) + (lane >> 3);            // + cb * 4
+    const int b_n = wn * WTN + (lane >> 3);                 // + cb * 4
 
     for (int s = 0; s < kDmStages - 1; s++) {
         if (s < k_tiles)
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(kDmThreads, DmCfg<BN>::kMinCtas)
             continue;
 #pragma unroll
         for (int cb = 0; cb < CBN; cb++) {
-            const long long n = n0 + wn * (BN / 2) + cb * 4 + (lane & 3);
+            const long long n = n0 + wn * WTN + cb * 4 + (lane & 3);
             if (n < N)
                 C[m * N + n] = double2{acc[rb][cb][0], acc[rb][cb][1]};
         }
@@ -358,10 +362,12 @@ int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, vo
             if (attr_err == cudaSuccess)
                 attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
         };
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 64>), DmCfg<64>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 64>), DmCfg<64>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 32>), DmCfg<32>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 32>), DmCfg<32>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 64, 4>), DmCfg<64>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 64, 4>), DmCfg<64>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 32, 4>), DmCfg<32>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 32, 4>), DmCfg<32>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 32, 2>), DmCfg<32>::kSmemBytes);
+        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 32, 2>), DmCfg<32>::kSmemBytes);
     });
     JB_CUDA(attr_err);
     const DmmaShape t = DmmaChoose(m, n, k);
@@ -374,20 +380,28 @@ int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, vo
     DmmaGather none;
     std::memset(&none, 0, sizeof(none));
     const double2 *pa = static_cast<const double2 *>(a), *pb = static_cast<const double2 *>(b);
-    if (t.bn == 64) {
+    if (t.bn == 32 && m <= 64) { // short M: two warps along M, four along N
         if (gather != nullptr)
-            GemmDmmaKernel<true, 64><<<grid, kDmThreads, DmCfg<64>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+            GemmDmmaKernel<true, 32, 2><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+                                                                                             t.k_tiles_per_split, *gather);
+        else
+            GemmDmmaKernel<false, 32, 2><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+                                                                                              t.k_tiles_per_split, none);
+    }
+    else if (t.bn == 64) {
+        if (gather != nullptr)
+            GemmDmmaKernel<true, 64, 4><<<grid, kDmThreads, DmCfg<64>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
                                                                                           t.k_tiles_per_split, *gather);
         else
-            GemmDmmaKernel<false, 64><<<grid, kDmThreads, DmCfg<64>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+            GemmDmmaKernel<false, 64, 4><<<grid, kDmThreads, DmCfg<64>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
                                                                                            t.k_tiles_per_split, none);
     }
     else {
         if (gather != nullptr)
-            GemmDmmaKernel<true, 32><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+            GemmDmmaKernel<true, 32, 4><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
                                                                                           t.k_tiles_per_split, *gather);
         else
-            GemmDmmaKernel<false, 32><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
+            GemmDmmaKernel<false, 32, 4><<<grid, kDmThreads, DmCfg<32>::kSmemBytes, stream>>>(pa, pb, dst, m, n, k, t.tiles_n,
                                                                                            t.k_tiles_per_split, none);
     }
     JB_CUDA(cudaGetLastError());
