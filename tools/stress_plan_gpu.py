@@ -1,7 +1,7 @@
 """Random tensor networks (random graph, random path, random sliced indices, optional open indices) through
 jb_plan_* on the GPU against the numpy oracle — exercises deferred slicing, fused chains of shared and per-slice
 steps, slice views and the FP64 accumulation on shapes no fixture covers.
-  python tools/stress_plan_gpu.py [trials] [only_trial | -1] [seed]"""
+  python tools/stress_plan_gpu.py [trials] [only_trial | -1] [seed] [big]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,15 +12,17 @@ from oracle import jet_oracle as jo  # noqa: E402  (checker)
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 only = int(sys.argv[2]) if len(sys.argv) > 2 else -1  # run just this trial (same random sequence), verbosely
 seed = int(sys.argv[3]) if len(sys.argv) > 3 else 31337
+big = len(sys.argv) > 4 and sys.argv[4] == "big"  # larger leaves / intermediates: reaches TTGT, tcgen05, DMMA
 rng = np.random.default_rng(seed)
 bad = ran = 0
 for trial in range(trials):
     dtype = np.complex64 if rng.integers(0, 2) else np.complex128
-    dims = int(rng.choice([2, 2, 2, 4]))
-    nt = int(rng.integers(3, 15))
+    dims = int(rng.choice([2, 2, 4, 8] if big else [2, 2, 2, 4]))
+    lgd = {2: 1, 4: 2, 8: 3}[dims]
+    nt = int(rng.integers(3, 9 if big else 15))
     # random connected multigraph: a spanning chain plus extra edges; every edge is an index shared by 2 tensors
     edges = [(i, i + 1) for i in range(nt - 1)]
-    for _ in range(int(rng.integers(0, nt + 3))):
+    for _ in range(int(rng.integers(0, (3 * nt if big else nt) + 3))):
         u, v = rng.choice(nt, 2, replace=False)
         edges.append((int(u), int(v)))
     idx_of = [[] for _ in range(nt)]
@@ -30,7 +32,7 @@ for trial in range(trials):
     n_open = int(rng.integers(0, 3)) if rng.integers(0, 4) == 0 else 0
     for o in range(n_open):
         idx_of[int(rng.integers(0, nt))].append(f"o{o}")
-    if max(len(x) for x in idx_of) * (1 if dims == 2 else 2) > 12:
+    if max(len(x) for x in idx_of) * lgd > (18 if big else 12):
         continue
     real = np.float32 if dtype == np.complex64 else np.float64
     tensors = []
@@ -51,7 +53,7 @@ for trial in range(trials):
         if rng.integers(0, 2):
             a, b = b, a
         new = node_idx[a] ^ node_idx[b]
-        if len(new) * (1 if dims == 2 else 2) > 20:
+        if len(new) * lgd > (23 if big else 20):
             too_big = True
             break
         path.append((a, b))
