@@ -49,3 +49,13 @@ if which in ("gemm_tc", "all_tc"):
     for _ in range(reps):
         ops.gemm_device(np.complex64, m, n, k, a.data_ptr(), b.data_ptr(), c.data_ptr(), ws.data_ptr(), wsb)
     torch.cuda.synchronize()
+if which in ("gemm_tc_skinny", "dot"):
+    m, n, k = (512, 1024, 1 << 16) if which == "gemm_tc_skinny" else (1, 1, 1 << 26)
+    a = torch.empty(m * k, dtype=torch.complex64, device=dev).normal_()
+    b = torch.empty(k * n, dtype=torch.complex64, device=dev).normal_()
+    c = torch.empty(m * n, dtype=torch.complex64, device=dev)
+    wsb = ops.gemm_ws_bytes(np.complex64, m, n, k)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+    for _ in range(reps):
+        ops.gemm_device(np.complex64, m, n, k, a.data_ptr(), b.data_ptr(), c.data_ptr(), ws.data_ptr(), wsb)
+    torch.cuda.synchronize()
