@@ -4,21 +4,33 @@
 // The public bookkeeping is the reference's (task names "<id>:<name>", ":results[r]" suffix on the
 // final step, name->tensor / name->parents maps, de-duplication of tasks by name across calls,
 // flops/memory counters, results + reduction result, Contract() -> std::future<void>).  What runs
-// inside Contract() is new: instead of one Taskflow host task per contraction that allocates a
-// fresh std::vector (TaskBasedContractor.hpp:386-390), the whole DAG is lowered once —
-//   * every named tensor gets an offset in ONE device arena, assigned from its lifetime when
-//     deletion tasks were requested (AddDeletionTasks becomes a plan-time analysis);
-//   * leaves are uploaded once, each unique contraction runs once as a fused GPU contraction
-//     (jb_contract: the operand transposes are folded into the kernel's loads), in task order on
-//     one stream with no host synchronisation in between;
-//   * results are reduced on the device in task order (deterministic);
-//   * tensors are copied back to the host only at the end, and only those the API exposes
-//     (everything without deletion tasks; just the results with them).
-// `num_threads` is accepted for source compatibility; the GPU stream replaces the thread pool.
+// inside Contract() is new.  The reference executes one Taskflow host task per contraction, each
+// allocating a fresh std::vector (TaskBasedContractor.hpp:386-390); its sliced benchmarks
+// (examples/paper_benchmarks/CPU/jet_cpu_m10/jet_sliced.cpp:69-93) add 2^s SliceIndices copies of one
+// network and rely on the de-duplication of equal task names (TaskBasedContractor.hpp:216-222) to share
+// the slice-independent work.  Here Contract()
+//   * groups the added networks by structure: copies made by TensorNetwork::SliceIndices differ only in
+//     the "idx(value)" annotations of their node names (TensorNetwork.hpp:266-274), so a group is one
+//     network + path + sliced indices, and every member is one slice id of it;
+//   * lowers each group to ONE device-resident plan set (jb_multi_*, include/jetb200.h): the unsliced
+//     leaves are rebuilt from the members and uploaded once, the slice-independent subtrees run once
+//     (the plan-time form of the name de-duplication), per-slice steps run as fused chains from a CUDA
+//     graph with several slices in flight, and the per-slice results are summed in FP64 on the device;
+//     unrelated networks each get their own plan;
+//   * copies back only what the API must expose at once: GetResults() and GetReductionResult().
+// GetNameToTensorMap() keeps the reference's contents (every intermediate of every network unless
+// deletion tasks were added), but those tensors are produced on first access: asking for the map after
+// Contract() replays the tasks one fused GPU contraction (jb_contract) per task and downloads them.
+// Environment: JET_B200_DEVICES="0,1,.."|"all" spreads slices over GPUs of this process,
+// JET_B200_LANES=n fixes the slices in flight per GPU (default: automatic), JET_B200_TBC=stepwise forces
+// the task-per-kernel path for everything.
+// `num_threads` is accepted for source compatibility; streams replace the thread pool.
 #pragma once
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <future>
 #include <map>
 #include <memory>
@@ -86,7 +98,14 @@ template <class TensorType> class TaskBasedContractor {
     }
 
     const NameToTaskMap &GetNameToTaskMap() const noexcept { return name_to_task_map_; }
-    const NameToTensorMap &GetNameToTensorMap() const noexcept { return name_to_tensor_map_; }
+    /// Every named tensor (nullptr while not computed / after deletion).  Intermediates are materialised on
+    /// the first call after Contract() (see the header comment); results and leaves are always in place.
+    const NameToTensorMap &GetNameToTensorMap() const
+    {
+        if (intermediates_pending_)
+            const_cast<TaskBasedContractor *>(this)->MaterialiseIntermediates_();
+        return name_to_tensor_map_;
+    }
     const NameToParentsMap &GetNameToParentsMap() const noexcept { return name_to_parents_map_; }
     const std::vector<TensorType> &GetResults() const noexcept { return results_; }
     const TensorType &GetReductionResult() const noexcept { return reduction_result_; }
@@ -107,6 +126,12 @@ template <class TensorType> class TaskBasedContractor {
         const size_t result_id = results_.size();
         results_.resize(result_id + 1);
 
+        NetworkRecord rec;
+        rec.result_id = result_id;
+        rec.num_leaves = num_leaves;
+        rec.path = path;
+        rec.leaves.resize(num_leaves);
+
         size_t shared = 0;
         for (size_t i = 0; i < path.size(); i++) {
             const auto [id_1, id_2] = path[i];
@@ -119,11 +144,17 @@ template <class TensorType> class TaskBasedContractor {
 
             name_to_parents_map_[name_1].emplace(name_3);
             name_to_parents_map_[name_2].emplace(name_3);
-            if (id_1 < num_leaves)
-                name_to_tensor_map_.try_emplace(name_1, std::make_unique<TensorType>(nodes[id_1].tensor));
-            if (id_2 < num_leaves)
-                name_to_tensor_map_.try_emplace(name_2, std::make_unique<TensorType>(nodes[id_2].tensor));
+            if (id_1 < num_leaves) {
+                const auto it = name_to_tensor_map_.try_emplace(name_1, std::make_unique<TensorType>(nodes[id_1].tensor)).first;
+                rec.leaves[id_1] = LeafRecord{it->second.get(), steps[id_1].node_indices};
+            }
+            if (id_2 < num_leaves) {
+                const auto it = name_to_tensor_map_.try_emplace(name_2, std::make_unique<TensorType>(nodes[id_2].tensor)).first;
+                rec.leaves[id_2] = LeafRecord{it->second.get(), steps[id_2].node_indices};
+            }
             name_to_tensor_map_.try_emplace(name_3, nullptr);
+            if (last)
+                rec.final_name = name_3;
 
             if (name_to_task_map_.count(name_3)) {
                 shared++;
@@ -146,6 +177,7 @@ template <class TensorType> class TaskBasedContractor {
                 storages_.push_back({name_3, result_id});
             }
         }
+        networks_.push_back(std::move(rec));
         return shared;
     }
 
@@ -194,6 +226,20 @@ template <class TensorType> class TaskBasedContractor {
         std::string name;
         size_t result_id;
     };
+    // one used leaf of an added network: its tensor (owned by name_to_tensor_map_; stable address) and the
+    // node's index labels, where sliced indices appear as "idx(value)" (TensorNetwork.hpp:266-274)
+    struct LeafRecord {
+        const TensorType *tensor = nullptr;
+        std::vector<std::string> node_indices;
+    };
+    // what one AddContractionTasks call described: enough to lower it onto a device plan
+    struct NetworkRecord {
+        size_t result_id = 0;
+        size_t num_leaves = 0;
+        PathInfo::Path path;
+        std::vector<LeafRecord> leaves; // indexed by node id; tensor == nullptr for leaves the path never touches
+        std::string final_name;
+    };
     struct DeviceTensor {
         std::vector<std::string> indices;
         std::vector<int64_t> extent;
@@ -219,6 +265,8 @@ template <class TensorType> class TaskBasedContractor {
     std::vector<Contraction> contractions_;
     std::vector<Storage> storages_;
     std::unordered_set<std::string> deleted_;
+    std::vector<NetworkRecord> networks_;
+    bool intermediates_pending_ = false;
 
     static std::string TaskName_(const PathStepInfo &step)
     {
@@ -271,12 +319,388 @@ template <class TensorType> class TaskBasedContractor {
         size_t top_ = 0;
     };
 
+    // ---- Contract(): plan sets for the results, tasks replayed one by one only for what they cannot give ----
     void Run_()
+    {
+        if (contractions_.empty() && storages_.empty())
+            return;
+        const char *mode = std::getenv("JET_B200_TBC");
+        const bool stepwise = mode != nullptr && std::string(mode) == "stepwise";
+        // names that must hold a tensor after Contract() besides the results: every contraction output that no
+        // deletion task removes
+        bool survivors = false;
+        for (const auto &c : contractions_)
+            survivors = survivors || (!deleted_.count(c.name_3) && !IsFinalName_(c.name_3));
+        if (stepwise || (delete_ && survivors)) {
+            // (deletion tasks cover only part of the graph: the leaves some surviving tensors would be
+            // re-derived from are gone after Contract(), so everything is produced now)
+            RunStepwise_(true);
+            intermediates_pending_ = false;
+            return;
+        }
+        RunPlans_();
+        for (const auto &net : networks_)
+            name_to_tensor_map_[net.final_name] = std::make_unique<TensorType>(results_[net.result_id]);
+        if (delete_)
+            for (const auto &name : deleted_)
+                name_to_tensor_map_[name] = nullptr;
+        intermediates_pending_ = survivors;
+    }
+
+    bool IsFinalName_(const std::string &name) const
+    {
+        for (const auto &s : storages_)
+            if (s.name == name)
+                return true;
+        return false;
+    }
+
+    void MaterialiseIntermediates_()
+    {
+        intermediates_pending_ = false;
+        RunStepwise_(false);
+    }
+
+    // ---- lowering onto plan sets -----------------------------------------------------------------------
+    struct Group {
+        std::vector<size_t> members; // indices into networks_, in the order they were added
+    };
+
+    // "idx(value)" -> (idx, value) for a node label that is not an index of the tensor
+    static bool ParseSliced_(const std::string &label, std::string *index, size_t *value)
+    {
+        if (label.size() < 4 || label.back() != ')')
+            return false;
+        const size_t open = label.rfind('(');
+        if (open == std::string::npos || open == 0 || open + 2 >= label.size())
+            return false; // needs a name before '(' and at least one digit inside
+        size_t v = 0;
+        for (size_t i = open + 1; i + 1 < label.size(); i++) {
+            if (label[i] < '0' || label[i] > '9')
+                return false;
+            v = v * 10 + static_cast<size_t>(label[i] - '0');
+        }
+        *index = label.substr(0, open);
+        *value = v;
+        return true;
+    }
+
+    // the structure of a network with the slice values blanked out: equal keys <=> slices of one network
+    static std::string StructureKey_(const NetworkRecord &net)
+    {
+        std::string key;
+        key.reserve(64 * net.leaves.size());
+        for (const auto &[a, b] : net.path) {
+            key += std::to_string(a);
+            key += ',';
+            key += std::to_string(b);
+            key += ';';
+        }
+        for (const auto &leaf : net.leaves) {
+            key += '|';
+            if (leaf.tensor == nullptr)
+                continue;
+            const auto &tidx = leaf.tensor->GetIndices();
+            for (const auto &label : leaf.node_indices) {
+                std::string index;
+                size_t value = 0;
+                if (std::find(tidx.begin(), tidx.end(), label) == tidx.end() && ParseSliced_(label, &index, &value)) {
+                    key += index;
+                    key += "(*)";
+                }
+                else {
+                    key += label;
+                }
+                key += ' ';
+            }
+            key += '/';
+            for (size_t i = 0; i < tidx.size(); i++) {
+                key += tidx[i];
+                key += ':';
+                key += std::to_string(leaf.tensor->GetShape()[i]);
+                key += ' ';
+            }
+        }
+        return key;
+    }
+
+    static std::vector<int> DevicesFromEnv_()
+    {
+        std::vector<int> devices;
+        const char *e = std::getenv("JET_B200_DEVICES");
+        if (e == nullptr || e[0] == 0)
+            return {0};
+        if (std::string(e) == "all") {
+            int n = 1;
+            JET_JB_CHECK(jb_device_count(&n));
+            for (int d = 0; d < n; d++)
+                devices.push_back(d);
+            return devices;
+        }
+        int cur = -1;
+        for (const char *c = e;; c++) {
+            if (*c >= '0' && *c <= '9') {
+                cur = (cur < 0 ? 0 : cur * 10) + (*c - '0');
+            }
+            else {
+                if (cur >= 0)
+                    devices.push_back(cur);
+                cur = -1;
+                if (*c == 0)
+                    break;
+            }
+        }
+        return devices.empty() ? std::vector<int>{0} : devices;
+    }
+
+    struct MultiGuard {
+        jb_multi *m = nullptr;
+        ~MultiGuard() { jb_multi_destroy(m); }
+    };
+
+    void RunPlans_()
+    {
+        constexpr int dtype = TensorHelpers::DtypeCode<scalar_t>();
+        using R = typename scalar_t::value_type;
+
+        // ---- group the networks by structure (first-seen order) ----------------------------------------
+        std::vector<Group> groups;
+        {
+            std::unordered_map<std::string, size_t> group_of;
+            for (size_t n = 0; n < networks_.size(); n++) {
+                const auto it = group_of.emplace(StructureKey_(networks_[n]), groups.size()).first;
+                if (it->second == groups.size())
+                    groups.emplace_back();
+                groups[it->second].members.push_back(n);
+            }
+        }
+        const std::vector<int> devices = DevicesFromEnv_();
+        int lanes = 0;
+        if (const char *e = std::getenv("JET_B200_LANES"))
+            lanes = std::max(0, std::min(5, std::atoi(e)));
+
+        // the reduction over the first reduce_count_ results, in double, in the index order of result 0
+        std::vector<double> total;
+        std::vector<std::string> total_indices;
+        std::vector<size_t> total_shape;
+
+        for (const Group &group : groups) {
+            const NetworkRecord &first = networks_[group.members[0]];
+            // ---- sliced indices of the group: labels of the first member, digits of every member --------
+            std::vector<std::string> sliced_names;
+            std::unordered_map<std::string, size_t> sliced_pos;
+            struct LeafSlicing {
+                std::vector<size_t> label_pos;  // positions in node_indices that carry "idx(v)"
+                std::vector<size_t> sliced_ids; // which sliced index each of them is
+            };
+            std::vector<LeafSlicing> leaf_slicing(first.leaves.size());
+            for (size_t l = 0; l < first.leaves.size(); l++) {
+                const LeafRecord &leaf = first.leaves[l];
+                if (leaf.tensor == nullptr)
+                    continue;
+                const auto &tidx = leaf.tensor->GetIndices();
+                for (size_t q = 0; q < leaf.node_indices.size(); q++) {
+                    std::string index;
+                    size_t value = 0;
+                    if (std::find(tidx.begin(), tidx.end(), leaf.node_indices[q]) != tidx.end() ||
+                        !ParseSliced_(leaf.node_indices[q], &index, &value))
+                        continue;
+                    const auto it = sliced_pos.emplace(index, sliced_names.size()).first;
+                    if (it->second == sliced_names.size())
+                        sliced_names.push_back(index);
+                    leaf_slicing[l].label_pos.push_back(q);
+                    leaf_slicing[l].sliced_ids.push_back(it->second);
+                }
+            }
+            const size_t ns = sliced_names.size();
+            std::vector<std::vector<size_t>> digits(group.members.size(), std::vector<size_t>(ns, 0));
+            std::vector<int64_t> dims(ns, 1);
+            for (size_t g = 0; g < group.members.size(); g++) {
+                const NetworkRecord &net = networks_[group.members[g]];
+                for (size_t l = 0; l < net.leaves.size(); l++)
+                    for (size_t q = 0; q < leaf_slicing[l].label_pos.size(); q++) {
+                        std::string index;
+                        size_t value = 0;
+                        ParseSliced_(net.leaves[l].node_indices[leaf_slicing[l].label_pos[q]], &index, &value);
+                        digits[g][leaf_slicing[l].sliced_ids[q]] = value;
+                        dims[leaf_slicing[l].sliced_ids[q]] =
+                            std::max<int64_t>(dims[leaf_slicing[l].sliced_ids[q]], static_cast<int64_t>(value) + 1);
+                    }
+            }
+
+            // ---- the unsliced network: used leaves only, sliced axes restored in front --------------------
+            std::unordered_map<std::string, int32_t> label;
+            std::vector<std::string> names;
+            auto mode_of = [&](const std::string &index) {
+                const auto it = label.emplace(index, static_cast<int32_t>(label.size())).first;
+                if (static_cast<size_t>(it->second) == names.size())
+                    names.push_back(index);
+                return it->second;
+            };
+            std::vector<int32_t> sliced_modes;
+            for (const auto &name : sliced_names)
+                sliced_modes.push_back(mode_of(name));
+            std::vector<int32_t> new_id(first.num_leaves + first.path.size(), -1);
+            std::vector<int32_t> rank, mode;
+            std::vector<int64_t> extent;
+            std::vector<const void *> data;
+            std::vector<std::vector<scalar_t>> rebuilt; // storage of the leaves that had to be reassembled
+            rebuilt.reserve(first.leaves.size());
+            int32_t used = 0;
+            for (size_t l = 0; l < first.leaves.size(); l++) {
+                const LeafRecord &leaf = first.leaves[l];
+                if (leaf.tensor == nullptr)
+                    continue;
+                new_id[l] = used++;
+                const LeafSlicing &ls = leaf_slicing[l];
+                rank.push_back(static_cast<int32_t>(ls.sliced_ids.size() + leaf.tensor->GetIndices().size()));
+                size_t blocks = 1;
+                for (const size_t sid : ls.sliced_ids) {
+                    mode.push_back(sliced_modes[sid]);
+                    extent.push_back(dims[sid]);
+                    blocks *= static_cast<size_t>(dims[sid]);
+                }
+                for (size_t i = 0; i < leaf.tensor->GetIndices().size(); i++) {
+                    mode.push_back(mode_of(leaf.tensor->GetIndices()[i]));
+                    extent.push_back(static_cast<int64_t>(leaf.tensor->GetShape()[i]));
+                }
+                if (ls.sliced_ids.empty()) {
+                    data.push_back(leaf.tensor->GetData().data());
+                    continue;
+                }
+                // block b of the rebuilt leaf = the member whose digits ravel to b (row-major over the leaf's own
+                // sliced axes); blocks no member selects stay zero and are never read
+                const size_t elems = leaf.tensor->GetSize();
+                rebuilt.emplace_back(blocks * elems);
+                std::vector<char> filled(blocks, 0);
+                for (size_t g = 0; g < group.members.size(); g++) {
+                    size_t b = 0;
+                    for (const size_t sid : ls.sliced_ids)
+                        b = b * static_cast<size_t>(dims[sid]) + digits[g][sid];
+                    if (filled[b])
+                        continue;
+                    filled[b] = 1;
+                    const TensorType *t = networks_[group.members[g]].leaves[l].tensor;
+                    std::memcpy(rebuilt.back().data() + b * elems, t->GetData().data(), sizeof(scalar_t) * elems);
+                }
+                data.push_back(rebuilt.back().data());
+            }
+            std::vector<int32_t> flat_path;
+            for (size_t i = 0; i < first.path.size(); i++) {
+                new_id[first.num_leaves + i] = used + static_cast<int32_t>(i);
+                flat_path.push_back(new_id[first.path[i].first]);
+                flat_path.push_back(new_id[first.path[i].second]);
+            }
+            std::vector<int64_t> slice_ids(group.members.size(), 0);
+            for (size_t g = 0; g < group.members.size(); g++)
+                for (size_t q = 0; q < ns; q++)
+                    slice_ids[g] = slice_ids[g] * dims[q] + static_cast<int64_t>(digits[g][q]);
+
+            jb_network_desc_t d{};
+            d.dtype = dtype;
+            d.device = devices[0];
+            d.num_leaves = used;
+            d.rank = rank.data();
+            d.extent = extent.data();
+            d.mode = mode.data();
+            d.h_data = data.data();
+            d.num_steps = static_cast<int32_t>(first.path.size());
+            d.path = flat_path.data();
+            d.num_sliced = static_cast<int32_t>(ns);
+            d.sliced_modes = sliced_modes.data();
+            d.flags = JB_PLAN_STORE_RESULTS;
+            MultiGuard guard;
+            const int nd = static_cast<int>(std::min<size_t>(devices.size(), group.members.size()));
+            JET_JB_CHECK(jb_multi_create(&d, nd, devices.data(), lanes, &guard.m));
+            rebuilt.clear(); // uploaded
+            jb_plan_stats_t stats;
+            JET_JB_CHECK(jb_multi_stats(guard.m, &stats));
+            JET_JB_CHECK(jb_multi_run_list(guard.m, slice_ids.data(), static_cast<int64_t>(slice_ids.size())));
+
+            // ---- results ------------------------------------------------------------------------------------
+            std::vector<std::string> indices;
+            std::vector<size_t> shape;
+            for (int i = 0; i < stats.result_rank; i++) {
+                indices.push_back(names[static_cast<size_t>(stats.result_modes[i])]);
+                shape.push_back(static_cast<size_t>(stats.result_extent[i]));
+            }
+            const size_t elems = static_cast<size_t>(stats.result_elems);
+            std::vector<scalar_t> all(elems * group.members.size());
+            JET_JB_CHECK(jb_multi_slice_results(guard.m, all.data()));
+            bool all_reduced = reduced_, none_reduced = true;
+            for (size_t g = 0; g < group.members.size(); g++) {
+                const size_t rid = networks_[group.members[g]].result_id;
+                TensorType t(indices, shape);
+                std::memcpy(t.GetData().data(), all.data() + g * elems, sizeof(scalar_t) * elems);
+                results_[rid] = std::move(t);
+                all_reduced = all_reduced && rid < reduce_count_;
+                none_reduced = none_reduced && !(reduced_ && rid < reduce_count_);
+            }
+            if (none_reduced)
+                continue;
+            // ---- this group's share of the reduction: the device's FP64 sum when every member takes part --------
+            std::vector<double> part(2 * elems, 0.0);
+            if (all_reduced) {
+                JET_JB_CHECK(jb_multi_result(guard.m, part.data()));
+            }
+            else {
+                for (size_t g = 0; g < group.members.size(); g++) {
+                    if (networks_[group.members[g]].result_id >= reduce_count_)
+                        continue;
+                    for (size_t i = 0; i < elems; i++) {
+                        part[2 * i] += static_cast<double>(all[g * elems + i].real());
+                        part[2 * i + 1] += static_cast<double>(all[g * elems + i].imag());
+                    }
+                }
+            }
+            if (total.empty()) {
+                total = std::move(part);
+                total_indices = indices;
+                total_shape = shape;
+                continue;
+            }
+            JET_ABORT_IF_NOT(total.size() == part.size() &&
+                                 Utilities::VectorDisjunctiveUnion(indices, total_indices).empty(),
+                             "Tensor addition with disjoint indices is not supported.");
+            if (indices == total_indices) {
+                for (size_t i = 0; i < total.size(); i++)
+                    total[i] += part[i];
+                continue;
+            }
+            // align to the first result's index order (AddTensors semantics, Tensor.hpp:200-215)
+            const size_t rk = indices.size();
+            std::vector<size_t> src_stride(rk, 1), perm(rk);
+            for (size_t j = rk; j-- > 1;)
+                src_stride[j - 1] = src_stride[j] * shape[j];
+            for (size_t j = 0; j < rk; j++)
+                perm[j] = static_cast<size_t>(std::find(indices.begin(), indices.end(), total_indices[j]) - indices.begin());
+            std::vector<size_t> counter(rk, 0);
+            for (size_t i = 0; i < elems; i++) {
+                size_t src = 0;
+                for (size_t j = 0; j < rk; j++)
+                    src += counter[j] * src_stride[perm[j]];
+                total[2 * i] += part[2 * src];
+                total[2 * i + 1] += part[2 * src + 1];
+                for (size_t j = rk; j-- > 0;) {
+                    if (++counter[j] < total_shape[j])
+                        break;
+                    counter[j] = 0;
+                }
+            }
+        }
+        if (reduced_ && !total.empty()) {
+            TensorType out(total_indices, total_shape);
+            for (size_t i = 0; i < out.GetSize(); i++)
+                out[i] = scalar_t{static_cast<R>(total[2 * i]), static_cast<R>(total[2 * i + 1])};
+            reduction_result_ = std::move(out);
+        }
+    }
+
+    // ---- one fused GPU contraction per task (jb_contract), every named tensor downloaded ------------------
+    void RunStepwise_(bool write_results)
     {
         constexpr int dtype = TensorHelpers::DtypeCode<scalar_t>();
         constexpr size_t eb = sizeof(scalar_t);
-        if (contractions_.empty() && storages_.empty())
-            return;
 
         // ---- describe every named tensor ------------------------------------------------------
         std::unordered_map<std::string, int32_t> label;
@@ -418,8 +842,9 @@ template <class TensorType> class TaskBasedContractor {
             JET_JB_CHECK(jb_memcpy_d2h(t.GetData().data(), at(off), eb * d.elems, g.stream));
             return t;
         };
-        for (const auto &s : storages_)
-            results_[s.result_id] = download(dt.at(s.name), dt.at(s.name).offset);
+        if (write_results)
+            for (const auto &s : storages_)
+                results_[s.result_id] = download(dt.at(s.name), dt.at(s.name).offset);
         for (const auto &c : contractions_) {
             if (delete_ && deleted_.count(c.name_3))
                 name_to_tensor_map_[c.name_3] = nullptr;
@@ -430,7 +855,7 @@ template <class TensorType> class TaskBasedContractor {
         if (delete_)
             for (const auto &name : deleted_)
                 name_to_tensor_map_[name] = nullptr;
-        if (acc_elems > 0)
+        if (acc_elems > 0 && write_results)
             reduction_result_ = download(dt.at(storages_[0].name), acc_off);
         JET_JB_CHECK(jb_stream_sync(g.stream));
     }

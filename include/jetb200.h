@@ -237,6 +237,8 @@ int jb_plan_run_list(jb_plan *plan, const int64_t *slice_ids, int64_t count);
 int jb_plan_result(jb_plan *plan, double *h_out);
 /* With JB_PLAN_STORE_RESULTS: result of the ordinal-th slice run since reset, in dtype. */
 int jb_plan_slice_result(jb_plan *plan, int64_t ordinal, void *h_out);
+/* The same for `count` consecutive ordinals in one copy (what GetResults() of the task-based contractor reads). */
+int jb_plan_slice_results(jb_plan *plan, int64_t first_ordinal, int64_t count, void *h_out);
 /* With JB_PLAN_KEEP_INTERMEDIATES: copy node `node`'s tensor (last slice run) to the host. */
 int jb_plan_node(jb_plan *plan, int32_t node, void *h_out, int64_t *elems);
 int jb_plan_sync(jb_plan *plan);
@@ -245,6 +247,14 @@ int jb_plan_sync(jb_plan *plan);
 int jb_plan_last_ms(jb_plan *plan, float *ms);
 /* The stream the plan launches on (cudaStream_t). */
 int jb_plan_stream(jb_plan *plan, void **stream);
+/* A second plan of the same network on `device` (any device of this process): the host-side plan (steps,
+ * fused chains, arena offsets) is copied, the arena / stream / CUDA graphs are new; upload the leaves with
+ * jb_plan_upload.  What LanePlans / SlicedContractor lanes and the multi-device set below are built from. */
+int jb_plan_clone(const jb_plan *plan, int device, jb_plan **clone);
+/* Device pointer of the plan's FP64 accumulator: `elems` (re, im) pairs of doubles, valid in stream order on
+ * jb_plan_stream — the buffer a reduction over GPUs reads (jb_reduce_sum), with no host staging. */
+int jb_plan_accumulator(jb_plan *plan, void **d_acc, int64_t *elems);
+int jb_plan_device(const jb_plan *plan, int *device);
 /* Per-step description for roofline accounting: fills up to cap entries. */
 typedef struct jb_step_info_t {
     int32_t node_a, node_b, node_c;
@@ -276,6 +286,57 @@ typedef struct jb_op_info_t {
 int jb_plan_ops(const jb_plan *plan, jb_op_info_t *ops, int32_t cap, int32_t *count);
 /* Like jb_plan_profile, per launch unit: ms[i] is the mean device time of unit i. */
 int jb_plan_profile_ops(jb_plan *plan, int64_t slice, int reps, float *ms, int32_t cap);
+
+
+/* ---- one network over several plans: lanes x devices of ONE process -----------------------------------------
+ * Replaces the Taskflow executor's worker pool (include/jet/TaskBasedContractor.hpp:322: tasks of different
+ * slices run on different workers) and the tf::reduce over the per-slice results
+ * (TaskBasedContractor.hpp:258-280): `lanes` plans per device keep that many slices in flight on one GPU
+ * (one arena, stream and CUDA graph each), every listed device gets such a group, a run deals contiguous
+ * blocks of the slice range to the plans in (device, lane) order, and the FP64 partial sums are added on the
+ * devices in that fixed order (peer copies over NVLink) — deterministic for a given (devices, lanes).
+ * devices == NULL means desc->device, desc->device + 1, ...; lanes == 0 picks the lane count from the plan's
+ * arena size (4 lanes below 512 MiB, 2 below 8 GiB, else 1; never more than fit in free device memory). */
+typedef struct jb_multi jb_multi;
+int jb_multi_create(const jb_network_desc_t *desc, int num_devices, const int *devices, int lanes,
+                    jb_multi **multi);
+int jb_multi_destroy(jb_multi *multi);
+int jb_multi_stats(const jb_multi *multi, jb_plan_stats_t *stats); /* of one plan */
+int jb_multi_num_plans(const jb_multi *multi, int *num_devices, int *lanes);
+int jb_multi_plan(jb_multi *multi, int index, jb_plan **plan); /* index = device_pos * lanes + lane */
+int jb_multi_upload(jb_multi *multi, const void *const *h_data);
+int jb_multi_reset(jb_multi *multi);
+/* reset + enqueue slices [first, first + count) / the listed ids on all plans (asynchronous) */
+int jb_multi_run(jb_multi *multi, int64_t first_slice, int64_t count);
+int jb_multi_run_list(jb_multi *multi, const int64_t *slice_ids, int64_t count);
+int jb_multi_sync(jb_multi *multi);
+/* Sum over everything run since the reset (after jb_multi_reduce: over all ranks), as doubles. */
+int jb_multi_result(jb_multi *multi, double *h_out);
+/* With JB_PLAN_STORE_RESULTS: the result of the ordinal-th slice of the last run. */
+int jb_multi_slice_result(jb_multi *multi, int64_t ordinal, void *h_out);
+/* ... and of ALL slices of the last run, in run order (count * result_elems elements of dtype). */
+int jb_multi_slice_results(jb_multi *multi, void *h_out);
+int jb_multi_last_ms(jb_multi *multi, float *ms); /* the slowest plan */
+
+/* ---- reduction across processes (one process per GPU): NCCL over NVLink / NVSwitch -----------------------------
+ * The reference has no multi-process layer; its sliced runs sum per-slice results with tf::reduce inside one
+ * process (TaskBasedContractor.hpp:258-280).  Here every rank contracts its block of slices and ONE
+ * ncclReduce of the FP64 partial sums (enqueued on the plan's stream, device buffers in and out) ends the job.
+ * NCCL is bound at run time (dlopen of libnccl.so.2; JB_NCCL_LIB overrides the path) — a process that already
+ * holds NCCL (torch.distributed) shares its copy.  Rank 0 calls jb_comm_unique_id and distributes the
+ * JB_COMM_ID_BYTES bytes by any means (MPI, a file, torch.distributed); then every rank calls jb_comm_create. */
+#define JB_COMM_ID_BYTES 128
+typedef struct jb_comm jb_comm;
+int jb_comm_unique_id(void *id128);
+int jb_comm_create(int world, int rank, const void *id128, int device, jb_comm **comm);
+int jb_comm_destroy(jb_comm *comm);
+int jb_comm_info(const jb_comm *comm, int *world, int *rank, int *nccl_version);
+/* In-place sum of n_doubles doubles at d_buf over all ranks, into rank `root` (root < 0: into every rank),
+ * asynchronous on `stream`. */
+int jb_reduce_sum(jb_comm *comm, void *d_buf, int64_t n_doubles, int root, void *stream);
+/* The set's on-device total (see jb_multi_result) reduced over the ranks of `comm`, which must live on the
+ * set's first device; afterwards jb_multi_result returns the reduced sum on `root`. */
+int jb_multi_reduce(jb_multi *multi, jb_comm *comm, int root);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ Layers:
                  + LanePlans (several slices in flight on one GPU)
 """
 from ._lib import JetB200Error  # noqa: F401
-from .plan import ContractionPlan, LanePlans, NetworkFile  # noqa: F401
+from .plan import Communicator, ContractionPlan, LanePlans, MultiPlan, NetworkFile  # noqa: F401
 from . import ops  # noqa: F401
 
 __version__ = "0.1.0"

@@ -152,7 +152,11 @@ SYMBOLS = [
     "jb_plan_reset", "jb_plan_run", "jb_plan_run_list", "jb_plan_result", "jb_plan_slice_result",
     "jb_plan_node", "jb_plan_sync", "jb_plan_last_ms", "jb_plan_stream", "jb_plan_steps",
     "jb_plan_profile", "jb_plan_ops", "jb_plan_profile_ops", "jb_chain_info", "jb_contract_chain",
-    "jb_contract_chain_host",
+    "jb_contract_chain_host", "jb_plan_clone", "jb_plan_accumulator", "jb_plan_device", "jb_plan_slice_results",
+    "jb_multi_create", "jb_multi_destroy", "jb_multi_stats", "jb_multi_num_plans", "jb_multi_plan", "jb_multi_upload",
+    "jb_multi_reset", "jb_multi_run", "jb_multi_run_list", "jb_multi_sync", "jb_multi_result",
+    "jb_multi_slice_result", "jb_multi_slice_results", "jb_multi_last_ms", "jb_comm_unique_id", "jb_comm_create",
+    "jb_comm_destroy", "jb_comm_info", "jb_reduce_sum", "jb_multi_reduce",
 ]
 
 _lib = None
@@ -225,6 +229,30 @@ def lib():
         L.jb_contract_chain.argtypes = [C.POINTER(ChainDesc), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p,
                                         C.c_void_p]
         L.jb_contract_chain_host.argtypes = [C.POINTER(ChainDesc), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+        L.jb_plan_clone.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.jb_plan_accumulator.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        L.jb_plan_device.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        L.jb_plan_slice_results.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        L.jb_multi_create.argtypes = [C.POINTER(NetworkDesc), C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.jb_multi_destroy.argtypes = [C.c_void_p]
+        L.jb_multi_stats.argtypes = [C.c_void_p, C.POINTER(PlanStats)]
+        L.jb_multi_num_plans.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.jb_multi_plan.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.jb_multi_upload.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.jb_multi_reset.argtypes = [C.c_void_p]
+        L.jb_multi_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.jb_multi_run_list.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.jb_multi_sync.argtypes = [C.c_void_p]
+        L.jb_multi_result.argtypes = [C.c_void_p, C.c_void_p]
+        L.jb_multi_slice_result.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.jb_multi_slice_results.argtypes = [C.c_void_p, C.c_void_p]
+        L.jb_multi_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.jb_comm_unique_id.argtypes = [C.c_void_p]
+        L.jb_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.jb_comm_destroy.argtypes = [C.c_void_p]
+        L.jb_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.jb_reduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.jb_multi_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 

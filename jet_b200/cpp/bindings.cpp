@@ -198,7 +198,13 @@ template <class T> void BindContractors(py::module_ &m, const char *tbc_name, co
                       const std::vector<std::string> &, int, int, int>(),
              py::arg("tn"), py::arg("path"), py::arg("sliced_indices"), py::arg("device") = 0, py::arg("flags") = 0,
              py::arg("lanes") = 1)
+        .def(py::init<const Jet::TensorNetwork<tensor_t> &, const Jet::PathInfo::Path &,
+                      const std::vector<std::string> &, const std::vector<int> &, int, int>(),
+             py::arg("tn"), py::arg("path"), py::arg("sliced_indices"), py::arg("devices"), py::arg("flags") = 0,
+             py::arg("lanes") = 1)
         .def_property_readonly("num_slices", &SC::NumSlices)
+        .def_property_readonly("num_devices", &SC::NumDevices)
+        .def_property_readonly("num_lanes", &SC::NumLanes)
         .def_property_readonly("flops", &SC::GetFlops)
         .def("contract", [](SC &sc, size_t first, py::object count) {
             const size_t n = count.is_none() ? sc.NumSlices() - first : count.cast<size_t>();

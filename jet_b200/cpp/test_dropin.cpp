@@ -404,6 +404,173 @@ void TestTaskBasedContractor()
     }
 }
 
+
+// ---- TaskBasedContractor lowered onto plan sets: sliced copies, several groups, partial reductions -------------
+// (the flow of examples/paper_benchmarks/CPU/jet_cpu_m10/jet_sliced.cpp:69-93 on small random networks; every
+// number is checked against the same tasks replayed one kernel per task, JET_B200_TBC=stepwise)
+template <class T> void TestTaskBasedContractorLowering()
+{
+    using tensor_t = Tensor<T>;
+    using TN = TensorNetwork<tensor_t>;
+    const double tol = std::is_same_v<T, c64> ? 1e-5 : 1e-12;
+    unsigned seed = 12345;
+    auto rnd = [&seed]() {
+        seed = seed * 1664525u + 1013904223u;
+        return static_cast<typename T::value_type>((seed >> 8) & 0xffff) / 32768 - 1;
+    };
+    auto random_tensor = [&](const std::vector<std::string> &indices, const std::vector<size_t> &shape) {
+        tensor_t t(indices, shape);
+        for (size_t i = 0; i < t.GetSize(); i++)
+            t[i] = T(rnd(), rnd());
+        return t;
+    };
+    auto near_tensor = [&](const tensor_t &a, const tensor_t &b) {
+        if (a.GetIndices() != b.GetIndices() || a.GetShape() != b.GetShape())
+            return false;
+        double num = 0, den = 0;
+        for (size_t i = 0; i < a.GetSize(); i++) {
+            num += std::norm(std::complex<double>(a.GetData()[i]) - std::complex<double>(b.GetData()[i]));
+            den += std::norm(std::complex<double>(b.GetData()[i]));
+        }
+        return std::sqrt(num) <= tol * std::max(std::sqrt(den), 1e-30);
+    };
+    // a ladder: two rails of 5 rank-3/4 tensors, rungs r*, rail bonds a*/b*, open legs o0 (dim 3) and o1
+    TN tn;
+    const size_t L = 5;
+    for (size_t i = 0; i < L; i++) {
+        std::vector<std::string> ia = {"r" + std::to_string(i)}, ib = {"r" + std::to_string(i)};
+        std::vector<size_t> sa = {i == 2 ? size_t(3) : size_t(2)}, sb = sa;
+        if (i > 0) {
+            ia.push_back("a" + std::to_string(i - 1));
+            sa.push_back(2);
+            ib.push_back("b" + std::to_string(i - 1));
+            sb.push_back(i == 3 ? 4 : 2);
+        }
+        if (i + 1 < L) {
+            ia.push_back("a" + std::to_string(i));
+            sa.push_back(2);
+            ib.push_back("b" + std::to_string(i));
+            sb.push_back(i == 2 ? 4 : 2);
+        }
+        if (i == 0) {
+            ia.push_back("o0");
+            sa.push_back(3);
+        }
+        if (i == L - 1) {
+            ib.push_back("o1");
+            sb.push_back(2);
+        }
+        tn.AddTensor(random_tensor(ia, sa), {});
+        tn.AddTensor(random_tensor(ib, sb), {});
+    }
+    // path: contract rung pairs, then sweep
+    typename TN::Path path;
+    for (size_t i = 0; i < L; i++)
+        path.emplace_back(2 * i, 2 * i + 1);
+    size_t acc = 2 * L;
+    for (size_t i = 1; i < L; i++) {
+        path.emplace_back(acc, 2 * L + i);
+        acc = 3 * L + i - 1;
+    }
+    const std::vector<std::string> sliced = {"a1", "r2", "b2"}; // dims 2, 3, 4 -> 24 slices
+    const size_t num_slices = 24;
+    tensor_t full;
+    {
+        TN copy = tn;
+        full = copy.Contract(path);
+    }
+    auto build = [&](TaskBasedContractor<tensor_t> &tbc, size_t count, bool reduce_first) {
+        if (reduce_first)
+            tbc.AddReductionTask();
+        size_t shared = 0;
+        for (size_t v = 0; v < count; v++) {
+            TN slice = tn;
+            slice.SliceIndices(sliced, v);
+            shared += tbc.AddContractionTasks(slice, PathInfo(slice, path));
+        }
+        return shared;
+    };
+    { // all 24 slices: reduction == unsliced contraction; per-slice results == stepwise replay
+        TaskBasedContractor<tensor_t> tbc, ref;
+        const size_t shared = build(tbc, num_slices, false);
+        build(ref, num_slices, false);
+        CHECK(shared > 0);
+        tbc.AddReductionTask();
+        ref.AddReductionTask();
+        tbc.Contract().get();
+        setenv("JET_B200_TBC", "stepwise", 1);
+        ref.Contract().get();
+        unsetenv("JET_B200_TBC");
+        CHECK(tbc.GetResults().size() == num_slices);
+        bool all_near = true;
+        for (size_t v = 0; v < num_slices; v++)
+            all_near = all_near && near_tensor(tbc.GetResults()[v], ref.GetResults()[v]);
+        CHECK(all_near);
+        CHECK(near_tensor(tbc.GetReductionResult(), full));
+        CHECK(near_tensor(ref.GetReductionResult(), full));
+        // the name -> tensor map holds every intermediate of every slice once it is asked for
+        const auto &lazy = tbc.GetNameToTensorMap();
+        const auto &eager = ref.GetNameToTensorMap();
+        CHECK(lazy.size() == eager.size());
+        bool same = true;
+        for (const auto &[name, ptr] : eager) {
+            const auto it = lazy.find(name);
+            same = same && it != lazy.end() && (ptr == nullptr) == (it->second == nullptr) &&
+                   (ptr == nullptr || near_tensor(*it->second, *ptr));
+        }
+        CHECK(same);
+    }
+    { // a subset of the slices, deletion tasks, results added after the reduction task are not reduced
+        TaskBasedContractor<tensor_t> tbc;
+        build(tbc, 5, false);
+        tbc.AddReductionTask();
+        TN extra = tn;
+        extra.SliceIndices(sliced, 7);
+        tbc.AddContractionTasks(extra, PathInfo(extra, path));
+        tbc.AddDeletionTasks();
+        tbc.Contract().get();
+        CHECK(tbc.GetResults().size() == 6);
+        tensor_t want = tbc.GetResults()[0];
+        for (size_t v = 1; v < 5; v++)
+            want = want.AddTensor(tbc.GetResults()[v]);
+        const double keep = tol;
+        (void)keep;
+        CHECK(near_tensor(tbc.GetReductionResult(), want));
+        size_t alive = 0;
+        for (const auto &[name, ptr] : tbc.GetNameToTensorMap())
+            alive += ptr != nullptr;
+        CHECK(alive == 6); // only the six results survive the deletion tasks
+    }
+    { // two unrelated networks (two groups) whose results carry the same indices in different orders
+        TN n1, n2;
+        n1.AddTensor(random_tensor({"x", "k"}, {3, 4}), {});
+        n1.AddTensor(random_tensor({"k", "y"}, {4, 2}), {});
+        n2.AddTensor(random_tensor({"y", "q", "p"}, {2, 5, 2}), {});
+        n2.AddTensor(random_tensor({"q", "x", "p"}, {5, 3, 2}), {});
+        TaskBasedContractor<tensor_t> tbc;
+        tbc.AddContractionTasks(n1, PathInfo(n1, {{0, 1}}));
+        tbc.AddContractionTasks(n2, PathInfo(n2, {{0, 1}}));
+        tbc.AddReductionTask();
+        tbc.Contract().get();
+        TN c1 = n1, c2 = n2;
+        const tensor_t want = c1.Contract({{0, 1}}).AddTensor(c2.Contract({{0, 1}}));
+        CHECK(near_tensor(tbc.GetReductionResult(), want));
+        CHECK((tbc.GetResults()[1].GetIndices() == std::vector<std::string>{"y", "x"}));
+    }
+    { // SlicedContractor over every device of the process == over one device
+        int ndev = 1;
+        jb_device_count(&ndev);
+        std::vector<int> devices;
+        for (int d = 0; d < std::min(ndev, 4); d++)
+            devices.push_back(d);
+        SlicedContractor<tensor_t> one(tn, path, sliced), many(tn, path, sliced, devices, 0, 2);
+        CHECK(one.NumSlices() == num_slices && many.NumDevices() == static_cast<int>(devices.size()));
+        CHECK(near_tensor(one.Contract(), full));
+        CHECK(near_tensor(many.Contract(), full));
+        CHECK(near_tensor(many.Contract(3, 11), one.Contract(3, 11)));
+    }
+}
+
 // ---- TensorNetworkSerializer (reference test/Test_TensorNetworkIO.cpp) ------------------------------
 template <class T> void TestIO()
 {
@@ -498,6 +665,8 @@ int main(int argc, char **argv)
         TestTensorNetwork<c128>();
         TestPathInfo();
         TestTaskBasedContractor();
+        TestTaskBasedContractorLowering<c64>();
+        TestTaskBasedContractorLowering<c128>();
         TestIO<c64>();
         TestIO<c128>();
         if (argc > 1)

@@ -2,6 +2,7 @@
 // reference interfaces each one replaces).
 #include <map>
 #include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -34,12 +35,16 @@ int NumSMs()
     return sms[dev];
 }
 
+// Occupancy and the >48 KB dynamic shared-memory opt-in are properties of (device, kernel): a process that
+// drives several GPUs (jb_network_desc_t.device, jb_set_device) must query / set them on each one.
 int BlocksPerSM(const void *kernel, int threads, size_t dyn_smem)
 {
     static std::mutex mu;
-    static std::map<std::pair<const void *, size_t>, int> cache;
+    static std::map<std::tuple<int, const void *, size_t>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(mu);
-    const auto key = std::make_pair(kernel, dyn_smem);
+    const auto key = std::make_tuple(dev, kernel, dyn_smem);
     auto it = cache.find(key);
     if (it != cache.end())
         return it->second;
@@ -48,6 +53,21 @@ int BlocksPerSM(const void *kernel, int threads, size_t dyn_smem)
         n = 1;
     cache[key] = n;
     return n;
+}
+
+int EnsureDynamicSmem(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    int dev = 0;
+    JB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &have = done[std::make_pair(dev, kernel)];
+    if (have >= bytes)
+        return 0;
+    JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    have = bytes;
+    return 0;
 }
 
 namespace {

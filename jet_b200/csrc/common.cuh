@@ -52,6 +52,8 @@ int NumSMs();
 // Resident CTAs per SM of a kernel (cached per function pointer): persistent grids are sized as
 // NumSMs() * this so that every CTA of the grid is resident at once (no partial tail wave).
 int BlocksPerSM(const void *kernel, int threads, size_t dyn_smem);
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel)
+int EnsureDynamicSmem(const void *kernel, size_t bytes);
 template <typename K> inline int PersistentBlocksPerSM(K kernel, int threads, size_t dyn_smem)
 {
     return BlocksPerSM(reinterpret_cast<const void *>(kernel), threads, dyn_smem);

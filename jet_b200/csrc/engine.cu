@@ -106,6 +106,8 @@ struct DeviceState {
     long long next_id;  // slice id of the next graph launch (sequential mode)
     long long ordinal;  // slices accumulated since reset
     long long list_pos; // >= 0: take ids from the list
+    unsigned int ctas_done; // AccumulateKernel: CTAs that have finished their share of the current slice
+    unsigned int pad;
 };
 
 __device__ __forceinline__ long long CurrentSlice(const DeviceState *st, const long long *list)
@@ -113,14 +115,15 @@ __device__ __forceinline__ long long CurrentSlice(const DeviceState *st, const l
     return st->list_pos >= 0 ? list[st->list_pos] : st->next_id;
 }
 
-// grid (descriptors, chunks of kSliceChunk view elements)
+// grid (chunks of kSliceChunk view elements, descriptors): the chunk index is in grid.x (limit 2^31 - 1) so a
+// view of any size fits; the descriptor count (sliced leaves + deferred roots) stays far below 65535
 template <typename V>
 __global__ void __launch_bounds__(128)
     SliceLeavesKernel(V *__restrict__ arena, const SliceLeafDesc *__restrict__ descs,
                       const DeviceState *__restrict__ st, const long long *__restrict__ list)
 {
-    const SliceLeafDesc &d = descs[blockIdx.x];
-    const long long e0 = static_cast<long long>(blockIdx.y) * kSliceChunk;
+    const SliceLeafDesc &d = descs[blockIdx.y];
+    const long long e0 = static_cast<long long>(blockIdx.x) * kSliceChunk;
     if (e0 >= d.out_elems)
         return;
     const long long e1 = min(d.out_elems, e0 + kSliceChunk);
@@ -147,13 +150,16 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Grid-stride over the result elements; the CTA that finishes last advances the slice cursor (every CTA has
+// read `ordinal` before it counts itself done, so the update cannot race with a reader).
 template <typename C>
 __global__ void __launch_bounds__(256)
     AccumulateKernel(const C *__restrict__ result, double2 *__restrict__ acc, C *__restrict__ store,
                      long long elems, long long store_cap, DeviceState *st)
 {
     const long long ordinal = st->ordinal;
-    for (long long i = threadIdx.x; i < elems; i += blockDim.x) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) {
         const C v = result[i];
         double2 a = acc[i];
         a.x += static_cast<double>(v.x);
@@ -164,11 +170,19 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        st->ordinal = ordinal + 1;
-        if (st->list_pos >= 0)
-            st->list_pos = st->list_pos + 1;
-        else
-            st->next_id = st->next_id + 1;
+        bool last = true;
+        if (gridDim.x > 1) {
+            __threadfence();
+            last = atomicAdd(&st->ctas_done, 1u) == gridDim.x - 1;
+        }
+        if (last) {
+            st->ctas_done = 0;
+            st->ordinal = ordinal + 1;
+            if (st->list_pos >= 0)
+                st->list_pos = st->list_pos + 1;
+            else
+                st->next_id = st->next_id + 1;
+        }
     }
 }
 
@@ -289,8 +303,9 @@ int LaunchSliceViews(jb_plan *p)
     long long max_out = 1;
     for (const SliceLeafDesc &sd : p->slice_descs)
         max_out = std::max(max_out, sd.out_elems);
-    const dim3 n(static_cast<unsigned>(p->slice_descs.size()),
-                 static_cast<unsigned>((max_out + kSliceChunk - 1) / kSliceChunk), 1);
+    JB_REQUIRE(p->slice_descs.size() <= 65535, "plan: more than 65535 sliced leaves");
+    const dim3 n(static_cast<unsigned>((max_out + kSliceChunk - 1) / kSliceChunk),
+                 static_cast<unsigned>(p->slice_descs.size()), 1);
     if (p->dtype == JB_C64)
         SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off),
                                                           p->At<DeviceState>(p->state_off),
@@ -310,13 +325,15 @@ int EnqueueSliceBody(jb_plan *p)
         JB_TRY(LaunchOp(p, op));
     const bool store = (p->flags & JB_PLAN_STORE_RESULTS) != 0;
     const void *res = p->arena + p->nodes[p->result_node].offset;
+    const unsigned acc_grid = static_cast<unsigned>(
+        std::max<long long>(1, std::min<long long>((p->result_elems + 1023) / 1024, 4ll * NumSMs())));
     if (p->dtype == JB_C64)
-        AccumulateKernel<float2><<<1, 256, 0, p->stream>>>(
+        AccumulateKernel<float2><<<acc_grid, 256, 0, p->stream>>>(
             static_cast<const float2 *>(res), p->At<double2>(p->acc_off),
             store ? p->At<float2>(p->store_off) : nullptr, p->result_elems, p->store_cap,
             p->At<DeviceState>(p->state_off));
     else
-        AccumulateKernel<double2><<<1, 256, 0, p->stream>>>(
+        AccumulateKernel<double2><<<acc_grid, 256, 0, p->stream>>>(
             static_cast<const double2 *>(res), p->At<double2>(p->acc_off),
             store ? p->At<double2>(p->store_off) : nullptr, p->result_elems, p->store_cap,
             p->At<DeviceState>(p->state_off));
@@ -403,6 +420,49 @@ int RunSlices(jb_plan *p, long long first, long long list_pos, long long count)
     return 0;
 }
 
+
+// Everything a plan owns on its device: arena, stream, events, pinned staging.  Shared by jb_plan_create and
+// jb_plan_clone (the host-side plan is computed once and copied).
+int AllocDeviceResources(jb_plan *p)
+{
+    size_t free_b = 0, total_b = 0;
+    JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (p->arena_bytes > free_b) {
+        return Fail("plan: the contraction needs " + std::to_string(p->arena_bytes >> 20) +
+                    " MiB of device memory but only " + std::to_string(free_b >> 20) +
+                    " MiB are free; slice more indices");
+    }
+    JB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->arena), p->arena_bytes));
+    JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    JB_CUDA(cudaEventCreate(&p->ev0));
+    JB_CUDA(cudaEventCreate(&p->ev1));
+    JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_list), sizeof(long long) * p->list_cap * 2));
+    for (auto &e : p->ev_list)
+        JB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        size_t end = 0;
+        for (int i = 0; i < p->num_leaves; i++) {
+            const Node &n = p->nodes[i];
+            end = std::max(end, n.raw_offset + static_cast<size_t>(n.desc >= 0 ? n.raw_elems : n.elems) * p->eb);
+        }
+        constexpr size_t kStageMax = size_t(32) << 20;
+        if (end > 0 && end <= kStageMax && p->num_leaves > 1) {
+            p->stage_bytes = end;
+            JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_stage), end));
+            std::memset(p->h_stage, 0, end);
+            JB_CUDA(cudaEventCreateWithFlags(&p->ev_stage, cudaEventDisableTiming));
+        }
+    }
+    if (!p->slice_descs.empty())
+        JB_CUDA(cudaMemcpyAsync(p->arena + p->descs_off, p->slice_descs.data(),
+                                sizeof(SliceLeafDesc) * p->slice_descs.size(), cudaMemcpyHostToDevice,
+                                p->stream));
+    JB_CUDA(cudaMemsetAsync(p->arena + p->acc_off, 0, sizeof(double2) * p->result_elems, p->stream));
+    JB_CUDA(cudaMemsetAsync(p->arena + p->state_off, 0, sizeof(DeviceState), p->stream));
+
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -413,7 +473,12 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     JB_REQUIRE(d->dtype == JB_C64 || d->dtype == JB_C128, "plan: unknown dtype");
     JB_REQUIRE(d->num_leaves >= 1, "An empty tensor network cannot be contracted.");
     JB_CUDA(cudaSetDevice(d->device));
-    std::unique_ptr<jb_plan> up(new jb_plan());
+    // every early return below releases what the plan holds by then (constant-bank slot, stream, events,
+    // pinned buffers, arena): jb_plan_destroy tolerates partially initialised plans
+    struct PlanDeleter {
+        void operator()(jb_plan *q) const { jb_plan_destroy(q); }
+    };
+    std::unique_ptr<jb_plan, PlanDeleter> up(new jb_plan());
     jb_plan *p = up.get();
     p->dtype = d->dtype;
     p->device = d->device;
@@ -832,42 +897,6 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     }
     p->arena_bytes = alloc.Peak();
 
-    // ---- device resources ---------------------------------------------------------------------------
-    size_t free_b = 0, total_b = 0;
-    JB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (p->arena_bytes > free_b) {
-        return Fail("plan: the contraction needs " + std::to_string(p->arena_bytes >> 20) +
-                    " MiB of device memory but only " + std::to_string(free_b >> 20) +
-                    " MiB are free; slice more indices");
-    }
-    JB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->arena), p->arena_bytes));
-    JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    JB_CUDA(cudaEventCreate(&p->ev0));
-    JB_CUDA(cudaEventCreate(&p->ev1));
-    JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_list), sizeof(long long) * p->list_cap * 2));
-    for (auto &e : p->ev_list)
-        JB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    {
-        size_t end = 0;
-        for (int i = 0; i < p->num_leaves; i++) {
-            const Node &n = p->nodes[i];
-            end = std::max(end, n.raw_offset + static_cast<size_t>(n.desc >= 0 ? n.raw_elems : n.elems) * p->eb);
-        }
-        constexpr size_t kStageMax = size_t(32) << 20;
-        if (end > 0 && end <= kStageMax && p->num_leaves > 1) {
-            p->stage_bytes = end;
-            JB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_stage), end));
-            std::memset(p->h_stage, 0, end);
-            JB_CUDA(cudaEventCreateWithFlags(&p->ev_stage, cudaEventDisableTiming));
-        }
-    }
-    if (!p->slice_descs.empty())
-        JB_CUDA(cudaMemcpyAsync(p->arena + p->descs_off, p->slice_descs.data(),
-                                sizeof(SliceLeafDesc) * p->slice_descs.size(), cudaMemcpyHostToDevice,
-                                p->stream));
-    JB_CUDA(cudaMemsetAsync(p->arena + p->acc_off, 0, sizeof(double2) * p->result_elems, p->stream));
-    JB_CUDA(cudaMemsetAsync(p->arena + p->state_off, 0, sizeof(DeviceState), p->stream));
-
     // ---- statistics -----------------------------------------------------------------------------------
     jb_plan_stats_t &S = p->stats;
     std::memset(&S, 0, sizeof(S));
@@ -923,13 +952,58 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     }
     S.arena_bytes = p->arena_bytes;
 
+    JB_TRY(AllocDeviceResources(p));
     if (d->h_data != nullptr) {
-        const int rc = jb_plan_upload(p, d->h_data);
-        if (rc != 0) {
-            jb_plan_destroy(up.release());
-            return rc;
-        }
+        JB_TRY(jb_plan_upload(p, d->h_data));
     }
+    *out = up.release();
+    return 0;
+}
+
+
+int jb_plan_clone(const jb_plan *src, int device, jb_plan **out)
+{
+    JB_REQUIRE(src != nullptr && out != nullptr, "plan: null argument");
+    JB_CUDA(cudaSetDevice(device));
+    struct PlanDeleter {
+        void operator()(jb_plan *q) const { jb_plan_destroy(q); }
+    };
+    std::unique_ptr<jb_plan, PlanDeleter> up(new jb_plan());
+    jb_plan *p = up.get();
+    // host-side plan: copied; device-side resources: fresh
+    p->dtype = src->dtype;
+    p->device = device;
+    p->flags = src->flags;
+    p->eb = src->eb;
+    p->num_leaves = src->num_leaves;
+    p->nodes = src->nodes;
+    p->steps = src->steps;
+    p->shared_order = src->shared_order;
+    p->slice_order = src->slice_order;
+    p->ops = src->ops;
+    p->shared_ops = src->shared_ops;
+    p->sliced_modes = src->sliced_modes;
+    p->sliced_dims = src->sliced_dims;
+    p->num_slices = src->num_slices;
+    p->slice_descs = src->slice_descs;
+    p->arena_bytes = src->arena_bytes;
+    p->ws_off = src->ws_off;
+    p->ws_bytes = src->ws_bytes;
+    p->acc_off = src->acc_off;
+    p->store_off = src->store_off;
+    p->state_off = src->state_off;
+    p->list_off = src->list_off;
+    p->descs_off = src->descs_off;
+    p->store_cap = src->store_cap;
+    p->list_cap = src->list_cap;
+    p->result_elems = src->result_elems;
+    p->result_node = src->result_node;
+    p->stats = src->stats;
+    if (src->chain_slot >= 0) {
+        p->chain_slot = ChainAcquireSlot(device);
+        JB_REQUIRE(p->chain_slot >= 0, "plan: no free constant-bank slot for another plan on this device");
+    }
+    JB_TRY(AllocDeviceResources(p));
     *out = up.release();
     return 0;
 }
@@ -1074,6 +1148,21 @@ int jb_plan_slice_result(jb_plan *p, int64_t ordinal, void *h_out)
     return 0;
 }
 
+int jb_plan_slice_results(jb_plan *p, int64_t first_ordinal, int64_t count, void *h_out)
+{
+    JB_REQUIRE(p && (h_out || count == 0), "plan: null argument");
+    JB_REQUIRE(p->store_cap > 0, "plan: created without JB_PLAN_STORE_RESULTS");
+    JB_REQUIRE(first_ordinal >= 0 && count >= 0 && first_ordinal + count <= p->store_cap,
+               "plan: slice ordinal out of range");
+    if (count == 0)
+        return 0;
+    JB_CUDA(cudaSetDevice(p->device));
+    JB_CUDA(cudaMemcpyAsync(h_out, p->arena + p->store_off + p->eb * p->result_elems * first_ordinal,
+                            p->eb * p->result_elems * count, cudaMemcpyDeviceToHost, p->stream));
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
 int jb_plan_node(jb_plan *p, int32_t node, void *h_out, int64_t *elems)
 {
     JB_REQUIRE(p, "plan: null argument");
@@ -1107,6 +1196,22 @@ int jb_plan_stream(jb_plan *p, void **stream)
 {
     JB_REQUIRE(p && stream, "plan: null argument");
     *stream = p->stream;
+    return 0;
+}
+
+int jb_plan_accumulator(jb_plan *p, void **d_acc, int64_t *elems)
+{
+    JB_REQUIRE(p && d_acc, "plan: null argument");
+    *d_acc = p->arena + p->acc_off;
+    if (elems)
+        *elems = p->result_elems;
+    return 0;
+}
+
+int jb_plan_device(const jb_plan *p, int *device)
+{
+    JB_REQUIRE(p && device, "plan: null argument");
+    *device = p->device;
     return 0;
 }
 

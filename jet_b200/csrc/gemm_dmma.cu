@@ -355,21 +355,17 @@ int LaunchDmma(int64_t m, int64_t n, int64_t k, const void *a, const void *b, vo
                const DmmaGather *gather, cudaStream_t stream)
 {
     JB_REQUIRE(GemmDmmaEligible(JB_C128, m, n, k), "gemm: shape not eligible for the FP64 tensor-core kernel");
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        auto set = [](const void *f, size_t bytes) {
-            if (attr_err == cudaSuccess)
-                attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-        };
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 64, 4>), DmCfg<64>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 64, 4>), DmCfg<64>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 32, 4>), DmCfg<32>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 32, 4>), DmCfg<32>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<false, 32, 2>), DmCfg<32>::kSmemBytes);
-        set(reinterpret_cast<const void *>(GemmDmmaKernel<true, 32, 2>), DmCfg<32>::kSmemBytes);
-    });
-    JB_CUDA(attr_err);
+    {
+        const std::pair<const void *, size_t> kernels[] = {
+            {reinterpret_cast<const void *>(GemmDmmaKernel<false, 64, 4>), DmCfg<64>::kSmemBytes},
+            {reinterpret_cast<const void *>(GemmDmmaKernel<true, 64, 4>), DmCfg<64>::kSmemBytes},
+            {reinterpret_cast<const void *>(GemmDmmaKernel<false, 32, 4>), DmCfg<32>::kSmemBytes},
+            {reinterpret_cast<const void *>(GemmDmmaKernel<true, 32, 4>), DmCfg<32>::kSmemBytes},
+            {reinterpret_cast<const void *>(GemmDmmaKernel<false, 32, 2>), DmCfg<32>::kSmemBytes},
+            {reinterpret_cast<const void *>(GemmDmmaKernel<true, 32, 2>), DmCfg<32>::kSmemBytes}};
+        for (const auto &kb : kernels)
+            JB_TRY(EnsureDynamicSmem(kb.first, kb.second));
+    }
     const DmmaShape t = DmmaChoose(m, n, k);
     double2 *dst = static_cast<double2 *>(c);
     if (t.splits > 1) {

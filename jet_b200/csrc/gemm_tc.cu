@@ -513,16 +513,8 @@ int LaunchGemmTc(int64_t m, int64_t n, int64_t k, const void *a, const void *b, 
     const TcWs w = TcWorkspace(m, n, k);
     JB_REQUIRE(ws != nullptr && ws_bytes >= w.total, "gemm: tensor-core workspace too small");
     const bool pre = TcPreSplit(m, n, k);
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(GemmTf32x3Kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kTcSmemBytes));
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(GemmTf32x3Kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(kTcSmemBytes));
-    });
-    JB_CUDA(attr_err);
+    JB_TRY(EnsureDynamicSmem(reinterpret_cast<const void *>(GemmTf32x3Kernel<true>), kTcSmemBytes));
+    JB_TRY(EnsureDynamicSmem(reinterpret_cast<const void *>(GemmTf32x3Kernel<false>), kTcSmemBytes));
     unsigned char *wb = static_cast<unsigned char *>(ws);
     float *a_hi = reinterpret_cast<float *>(wb + w.a_hi), *a_lo = reinterpret_cast<float *>(wb + w.a_lo);
     float *b_hi = reinterpret_cast<float *>(wb + w.b_hi), *b_lo = reinterpret_cast<float *>(wb + w.b_lo);

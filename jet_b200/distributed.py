@@ -4,6 +4,10 @@ collective, and ONE reduce of the double-precision partial amplitudes closes the
 NVLink on GPUs, gloo in the CPU tests.  The reference has no inter-device path at all
 (reference include/jet/TaskBasedContractor.hpp:258-280 reduces inside one process)."""
 from __future__ import annotations
+# Two reduce paths: `reduce_on_device` (the product path on GPUs: jb_multi_reduce = ncclReduce of the FP64
+# on-device total, enqueued on the plan's stream, no host staging; the communicator is jet_b200.Communicator,
+# its id handed around by torch.distributed) and `reduce_amplitude` (host arrays through torch.distributed:
+# what the CPU gloo tests exercise, and a cross-check of the first on GPUs).
 
 from typing import Optional, Tuple
 
@@ -38,3 +42,28 @@ def reduce_amplitude(partial: np.ndarray, dst: int = 0, device=None) -> Optional
     if dist.get_rank() != dst:
         return None
     return t.cpu().numpy().view(np.complex128).reshape(partial.shape)
+
+
+def make_communicator(device: int):
+    """A jet_b200.Communicator (NCCL, bound inside libjetb200.so) spanning the initialised torch.distributed
+    group: rank 0's unique id travels as a broadcast object."""
+    import torch.distributed as dist
+
+    from .plan import Communicator
+
+    def exchange(ident):
+        box = [ident]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    return Communicator(dist.get_world_size(), dist.get_rank(), device, exchange)
+
+
+def reduce_on_device(plan, comm, root: int = 0) -> Optional[np.ndarray]:
+    """Finish a sliced run: the plan set's on-device FP64 total is reduced over the ranks by one ncclReduce on
+    the plan's stream; only `root` copies the 16 x result_elems bytes back.  Returns the total on root."""
+    plan.reduce(comm, root)
+    if comm.rank != root:
+        plan.sync()
+        return None
+    return plan.result()

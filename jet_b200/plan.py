@@ -237,29 +237,100 @@ class ContractionPlan:
         return self.result()
 
 
-class LanePlans:
-    """K ContractionPlans of the same sliced network on one GPU — each with its own arena, stream and
-    CUDA graph — so that K independent slice contractions are in flight at once: slice number j of a
-    run goes to lane j % K.  The reference runs the tasks of different slices concurrently on Taskflow
-    worker threads (include/jet/TaskBasedContractor.hpp:322, examples/paper_benchmarks/CPU/
-    jet_cpu_m10/jet_sliced.cpp:69-93); this is the same idea with streams.  It pays off when one slice
-    is too small to fill the GPU (m10, GBS fock4: every kernel is a handful of CTAs and the slice is
-    launch-latency bound); large slices (m12, m=20) gain nothing and should use one lane.
-    The result is the sum of the lanes' FP64 accumulators in lane order: deterministic for a given K."""
+class _PlanView(ContractionPlan):
+    """One plan of a MultiPlan, borrowed (profiling, streams): owned and destroyed by the set."""
+
+    def __init__(self, owner: "MultiPlan", handle):  # noqa: D401 - not calling ContractionPlan.__init__
+        self._h = handle
+        self._owner = owner
+        self.net, self.sliced, self.dtype = owner.net, owner.sliced, owner.dtype
+        self.stats, self.num_slices = owner.stats, owner.num_slices
+        self.result_elems, self.result_shape, self.result_indices = (owner.result_elems, owner.result_shape,
+                                                                     owner.result_indices)
+
+    def close(self):
+        self._h = None
+
+
+class MultiPlan:
+    """One sliced network on `lanes` plans per device over any number of devices of this process (wraps
+    jb_multi, include/jetb200.h).  Each plan has its own arena, stream and CUDA graphs, so `lanes` independent
+    slice contractions are in flight per GPU — the reference runs the tasks of different slices concurrently on
+    Taskflow worker threads (include/jet/TaskBasedContractor.hpp:322, examples/paper_benchmarks/CPU/
+    jet_cpu_m10/jet_sliced.cpp:69-93); this is the same idea with streams.  Lanes pay off when one slice is too
+    small to fill the GPU (m10, GBS fock4: launch-latency bound); large slices (m12, m=20) gain little.
+    A run deals CONTIGUOUS blocks of its slice list to the plans in (device, lane) order — the same rule as the
+    C++ Jet::SlicedContractor — and the FP64 partial sums are added on the devices in that order: the result is
+    deterministic for a given (devices, lanes).  `reduce(comm)` finishes a one-process-per-GPU job with one NCCL
+    reduce of the on-device total."""
 
     MAX_LANES = 5  # constant-bank slots available to plans (jet_b200/csrc/chain.cu)
 
-    def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), lanes: int = 2, device: int = 0, **kw):
-        if not 1 <= lanes <= self.MAX_LANES:
-            raise ValueError(f"lanes must be in 1..{self.MAX_LANES}")
-        self.plans = [ContractionPlan(net, sliced, device=device, **kw) for _ in range(lanes)]
-        p0 = self.plans[0]
-        self.num_slices, self.result_elems, self.result_shape = p0.num_slices, p0.result_elems, p0.result_shape
-        self.result_indices, self.stats, self.dtype = p0.result_indices, p0.stats, p0.dtype
+    def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), lanes: int = 2, device: int = 0,
+                 devices: Optional[Sequence[int]] = None, keep_intermediates=False, use_graph=True,
+                 store_results=False, path: Optional[Sequence[Sequence[int]]] = None, fuse=True):
+        if not 0 <= lanes <= self.MAX_LANES:
+            raise ValueError(f"lanes must be in 0..{self.MAX_LANES} (0 = automatic)")
+        self.net = net
+        self.sliced = list(sliced)
+        self.devices = [int(d) for d in (devices if devices is not None else [device])]
+        self.dtype = np.dtype(net.dtype)
+        labels: Dict[str, int] = {}
+        for idx, _ in net.tensors:
+            for i in idx:
+                labels.setdefault(i, len(labels))
+        self.label_names = {v: k for k, v in labels.items()}
+        for s in self.sliced:
+            if s not in labels:
+                raise ValueError("Sliced index does not exist.")
+        ranks = [arr.ndim for _, arr in net.tensors]
+        extents = [int(s) for _, arr in net.tensors for s in arr.shape]
+        modes = [labels[i] for idx, _ in net.tensors for i in idx]
+        self._leaves = [np.ascontiguousarray(arr, dtype=self.dtype) for _, arr in net.tensors]
+        steps = [list(p) for p in (net.path if path is None else path)]
+        flat_path = [v for p in steps for v in p]
+        n = len(ranks)
+        self._rank = (C.c_int32 * max(n, 1))(*ranks)
+        self._extent = (C.c_int64 * max(len(extents), 1))(*extents)
+        self._mode = (C.c_int32 * max(len(modes), 1))(*modes)
+        self._data = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in self._leaves])
+        self._path = (C.c_int32 * max(len(flat_path), 1))(*flat_path)
+        self._sliced = (C.c_int32 * max(len(self.sliced), 1))(*[labels[s] for s in self.sliced])
+        flags = (JB_PLAN_KEEP_INTERMEDIATES if keep_intermediates else 0) | (0 if use_graph else JB_PLAN_NO_GRAPH) | (
+            JB_PLAN_STORE_RESULTS if store_results else 0) | (0 if fuse else JB_PLAN_NO_FUSE)
+        desc = NetworkDesc(dtype_code(self.dtype), self.devices[0], n, self._rank, self._extent, self._mode, self._data,
+                           len(steps), self._path, len(self.sliced), self._sliced, flags)
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        check(lib().jb_multi_create(C.byref(desc), len(self.devices), devs, lanes, C.byref(self._h)))
+        st = PlanStats()
+        check(lib().jb_multi_stats(self._h, C.byref(st)))
+        nd, nl = C.c_int(), C.c_int()
+        check(lib().jb_multi_num_plans(self._h, C.byref(nd), C.byref(nl)))
+        self.lanes = int(nl.value)
+        self.stats = st
+        self.num_slices = int(st.num_slices)
+        self.result_elems = int(st.result_elems)
+        self.result_shape = [int(st.result_extent[i]) for i in range(st.result_rank)]
+        self.result_indices = [self.label_names[st.result_modes[i]] for i in range(st.result_rank)]
+        self.plans: List[_PlanView] = []
+        for i in range(nd.value * nl.value):
+            h = C.c_void_p()
+            check(lib().jb_multi_plan(self._h, i, C.byref(h)))
+            self.plans.append(_PlanView(self, h))
 
     def close(self):
-        for p in self.plans:
-            p.close()
+        if getattr(self, "_h", None) is not None and self._h:
+            for p in self.plans:
+                p.close()
+            lib().jb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
@@ -271,35 +342,84 @@ class LanePlans:
         return [p.stream() for p in self.plans]
 
     def upload_ptrs(self, ptrs: Sequence[int]):
-        for p in self.plans:
-            p.upload_ptrs(ptrs)
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        check(lib().jb_multi_upload(self._h, arr))
 
     def reset(self):
-        for p in self.plans:
-            p.reset()
+        check(lib().jb_multi_reset(self._h))
 
     def run_list(self, ids: Sequence[int]):
-        k = len(self.plans)
-        for lane, p in enumerate(self.plans):
-            mine = list(ids[lane::k])
-            if mine:
-                p.run_list(mine)
+        """reset + enqueue the listed slice ids (asynchronous)."""
+        arr = (C.c_int64 * max(len(ids), 1))(*[int(i) for i in ids])
+        check(lib().jb_multi_run_list(self._h, arr, len(ids)))
 
     def run(self, first: int = 0, count: Optional[int] = None):
+        """reset + enqueue slices first .. first + count - 1 (asynchronous)."""
         count = self.num_slices - first if count is None else count
-        self.run_list(range(first, first + count))
+        check(lib().jb_multi_run(self._h, first, count))
 
     def sync(self):
-        for p in self.plans:
-            p.sync()
+        check(lib().jb_multi_sync(self._h))
+
+    def reduce(self, comm: "Communicator", root: int = 0):
+        """Sum the set's on-device total over the ranks of `comm` (NCCL, on the first plan's stream)."""
+        check(lib().jb_multi_reduce(self._h, comm._h, root))
 
     def result(self) -> np.ndarray:
-        out = self.plans[0].result()
-        for p in self.plans[1:]:
-            out = out + p.result()
+        out = np.empty(self.result_elems, dtype=np.complex128)
+        check(lib().jb_multi_result(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(self.result_shape)
+
+    def slice_results(self, count: int) -> np.ndarray:
+        out = np.empty((count, self.result_elems), dtype=self.dtype)
+        check(lib().jb_multi_slice_results(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def last_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().jb_multi_last_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def amplitude(self, slice_ids: Optional[Sequence[int]] = None) -> np.ndarray:
-        self.reset()
-        self.run_list(list(range(self.num_slices)) if slice_ids is None else list(slice_ids))
+        if slice_ids is None:
+            self.run(0, self.num_slices)
+        else:
+            self.run_list(list(slice_ids))
         return self.result()
+
+
+LanePlans = MultiPlan  # the round-1 name (one device, several lanes)
+
+
+class Communicator:
+    """NCCL communicator of a one-process-per-GPU job (wraps jb_comm).  `exchange(id_bytes_or_None) -> bytes`
+    must hand rank 0's 128-byte id to every rank (e.g. a torch.distributed / MPI broadcast)."""
+
+    def __init__(self, world: int, rank: int, device: int, exchange):
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(lib().jb_comm_unique_id(buf))
+        ident = exchange(bytes(buf.raw) if rank == 0 else None)
+        assert len(ident) == 128
+        self._h = C.c_void_p()
+        check(lib().jb_comm_create(world, rank, C.c_char_p(ident), device, C.byref(self._h)))
+        self.world, self.rank, self.device = world, rank, device
+
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        check(lib().jb_comm_info(self._h, None, None, C.byref(v)))
+        return int(v.value)
+
+    def reduce_sum(self, d_ptr: int, n_doubles: int, root: int = 0, stream: int = 0):
+        check(lib().jb_reduce_sum(self._h, C.c_void_p(d_ptr), n_doubles, root, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().jb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -101,3 +101,61 @@ def test_cpp_dropin_binary(data_dir):
     print(p.stdout[-2000:], p.stderr[-4000:])
     assert p.returncode == 0, p.stderr[-4000:]
     assert " 0 failed" in p.stdout
+
+
+def _run(cmd, timeout=900, env=None):
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert p.returncode == 0, (cmd, p.stdout[-2000:], p.stderr[-4000:])
+    return p.stdout
+
+
+def _parse_result(stdout):
+    # "result=Size=1\nIndices={}\nData={(re,im)}" — the reference's Tensor operator<<
+    import re
+
+    m = re.search(r"Data=\{\(([-+0-9.eE]+),([-+0-9.eE]+)\)", stdout)
+    assert m, stdout[-500:]
+    return complex(float(m.group(1)), float(m.group(2)))
+
+
+def test_reference_jet_sliced_driver_on_the_plan_engine(data_dir):
+    """The reference's OWN benchmark driver (examples/paper_benchmarks/CPU/jet_cpu_m10/jet_sliced.cpp, compiled
+    from where it lies against include/ by `make -C jet_b200/cpp examples`): 64 SliceIndices copies ->
+    AddContractionTasks -> AddReductionTask -> Contract().wait() must give the reference's 64-slice sum."""
+    exe = os.path.join(ROOT, "jet_b200", "cpp", "examples", "jet_sliced_m10")
+    if not os.path.exists(exe):
+        pytest.skip("examples not built (needs /root/reference at build time)")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "amplitudes.json")))
+    out = _run([exe, os.path.join(data_dir, "m10.json"), "1", "6"])
+    got = _parse_result(out)
+    want = complex(gold["m10_s6_sum64_complex128"]["re"], gold["m10_s6_sum64_complex128"]["im"])
+    assert abs(got - want) / abs(want) < 1e-5, (got, want)
+    assert "number_of_slices = 64" in out
+
+
+def test_reference_jet_full_driver(data_dir):
+    exe = os.path.join(ROOT, "jet_b200", "cpp", "examples", "jet_full_m10")
+    if not os.path.exists(exe):
+        pytest.skip("examples not built (needs /root/reference at build time)")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "amplitudes.json")))
+    got = _parse_result(_run([exe, os.path.join(data_dir, "m10.json"), "1"]))
+    want = complex(gold["m10_full_complex64"]["re"], gold["m10_full_complex64"]["im"])
+    assert abs(got - want) / abs(want) < 2e-5, (got, want)
+
+
+@pytest.mark.parametrize("indices,n,key", [("p7,s7,h4,m1,m2,I2", 64, "m10_s6_sum64_complex128"),
+                                           ("p7,s7,h4,m1,m2,I2,V4,z2,t4,C1", 16, "m10_s10_sum_first16_complex128")])
+def test_tbc_flow_matches_sliced_contractor(data_dir, indices, n, key):
+    """TaskBasedContractor fed with SliceIndices copies (lowered onto plan sets) == SlicedContractor == golden."""
+    exe = os.path.join(ROOT, "jet_b200", "cpp", "tbc_bench")
+    assert os.path.exists(exe), "build with __graft_entry__.build()"
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "amplitudes.json")))
+    want = complex(gold[key]["re"], gold[key]["im"])
+    res = {}
+    for api in ("tbc", "sliced"):
+        line = _run([exe, os.path.join(data_dir, "m10.json"), indices, "--api", api, "--slices", str(n), "--reps", "2"])
+        res[api] = json.loads(line.strip().splitlines()[-1])
+        got = complex(*res[api]["result"])
+        assert abs(got - want) / abs(want) < 1e-5, (api, got, want)
+    assert res["tbc"]["shared_tasks"] > 0
+    print(res)
