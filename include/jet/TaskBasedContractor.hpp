@@ -611,11 +611,25 @@ template <class TensorType> class TaskBasedContractor {
             d.flags = JB_PLAN_STORE_RESULTS;
             MultiGuard guard;
             const int nd = static_cast<int>(std::min<size_t>(devices.size(), group.members.size()));
-            JET_JB_CHECK(jb_multi_create(&d, nd, devices.data(), lanes, &guard.m));
+            JET_JB_CHECK(jb_multi_create(&d, nd, devices.data(),
+                                         static_cast<int>(std::min<size_t>(lanes, group.members.size())), &guard.m));
             rebuilt.clear(); // uploaded
             jb_plan_stats_t stats;
             JET_JB_CHECK(jb_multi_stats(guard.m, &stats));
-            JET_JB_CHECK(jb_multi_run_list(guard.m, slice_ids.data(), static_cast<int64_t>(slice_ids.size())));
+            // a network added twice is one slice id: it runs once and its result is handed to every copy
+            std::vector<int64_t> run_ids;
+            std::vector<size_t> ordinal_of(group.members.size());
+            {
+                std::unordered_map<int64_t, size_t> seen;
+                for (size_t g = 0; g < group.members.size(); g++) {
+                    const auto it = seen.emplace(slice_ids[g], run_ids.size()).first;
+                    if (it->second == run_ids.size())
+                        run_ids.push_back(slice_ids[g]);
+                    ordinal_of[g] = it->second;
+                }
+            }
+            const bool duplicates = run_ids.size() != group.members.size();
+            JET_JB_CHECK(jb_multi_run_list(guard.m, run_ids.data(), static_cast<int64_t>(run_ids.size())));
 
             // ---- results ------------------------------------------------------------------------------------
             std::vector<std::string> indices;
@@ -625,13 +639,13 @@ template <class TensorType> class TaskBasedContractor {
                 shape.push_back(static_cast<size_t>(stats.result_extent[i]));
             }
             const size_t elems = static_cast<size_t>(stats.result_elems);
-            std::vector<scalar_t> all(elems * group.members.size());
+            std::vector<scalar_t> all(elems * run_ids.size());
             JET_JB_CHECK(jb_multi_slice_results(guard.m, all.data()));
-            bool all_reduced = reduced_, none_reduced = true;
+            bool all_reduced = reduced_ && !duplicates, none_reduced = true;
             for (size_t g = 0; g < group.members.size(); g++) {
                 const size_t rid = networks_[group.members[g]].result_id;
                 TensorType t(indices, shape);
-                std::memcpy(t.GetData().data(), all.data() + g * elems, sizeof(scalar_t) * elems);
+                std::memcpy(t.GetData().data(), all.data() + ordinal_of[g] * elems, sizeof(scalar_t) * elems);
                 results_[rid] = std::move(t);
                 all_reduced = all_reduced && rid < reduce_count_;
                 none_reduced = none_reduced && !(reduced_ && rid < reduce_count_);
@@ -648,8 +662,8 @@ template <class TensorType> class TaskBasedContractor {
                     if (networks_[group.members[g]].result_id >= reduce_count_)
                         continue;
                     for (size_t i = 0; i < elems; i++) {
-                        part[2 * i] += static_cast<double>(all[g * elems + i].real());
-                        part[2 * i + 1] += static_cast<double>(all[g * elems + i].imag());
+                        part[2 * i] += static_cast<double>(all[ordinal_of[g] * elems + i].real());
+                        part[2 * i + 1] += static_cast<double>(all[ordinal_of[g] * elems + i].imag());
                     }
                 }
             }

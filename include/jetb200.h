@@ -198,6 +198,8 @@ typedef struct jb_network_desc_t {
 #define JB_PLAN_NO_GRAPH 2           /* launch kernels directly instead of through a CUDA graph */
 #define JB_PLAN_STORE_RESULTS 4      /* keep every slice's own result (for GetResults()) */
 #define JB_PLAN_NO_FUSE 8            /* one kernel per path step: no fused contraction chains */
+#define JB_PLAN_DRY_RUN 16           /* host-side planning only (no device needed): stats / steps / ops work,
+                                        everything that would touch the GPU fails */
 
 typedef struct jb_plan_stats_t {
     int64_t num_slices;        /* product of sliced extents */
@@ -272,6 +274,10 @@ int jb_plan_profile(jb_plan *plan, int64_t slice, int reps, float *ms, int32_t c
 /* Launch units of one slice in execution order: a unit is one path step or a fused chain of path
  * steps.  bytes = what the unit must move (for a chain: first input + small operands + last
  * output); step_bytes = the step-by-step figure sizeof(T)*(MK+KN+MN) summed over its steps. */
+#define JB_GEMM_FMA 0      /* GemmKernel (+ SplitKReduceKernel): FP32 / FP64 FMA */
+#define JB_GEMM_SMALL_MN 1 /* SmallMnKernel: DOTU / GEMV corner with a long K */
+#define JB_GEMM_TCGEN05 2  /* GemmTf32x3Kernel: tcgen05 3xTF32 (complex64) */
+#define JB_GEMM_DMMA 3     /* GemmDmmaKernel: FP64 tensor pipe (complex128) */
 typedef struct jb_op_info_t {
     int32_t kernel;     /* 0 stream, 1 ttgt, 2 fused chain */
     int32_t n_steps;    /* path steps executed by this unit */
@@ -280,7 +286,7 @@ typedef struct jb_op_info_t {
     int32_t log_tile;   /* fused chain: log2 of the shared-memory tile (elements) */
     int32_t launches;
     int32_t n_stages;   /* fused chain: barrier-separated stages */
-    int32_t pad;
+    int32_t gemm_kind;  /* ttgt: JB_GEMM_* — the GEMM kernel this unit launches */
     double flops, bytes, step_bytes;
 } jb_op_info_t;
 int jb_plan_ops(const jb_plan *plan, jb_op_info_t *ops, int32_t cap, int32_t *count);

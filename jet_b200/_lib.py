@@ -18,6 +18,7 @@ JB_PLAN_KEEP_INTERMEDIATES = 1
 JB_PLAN_NO_GRAPH = 2
 JB_PLAN_STORE_RESULTS = 4
 JB_PLAN_NO_FUSE = 8
+JB_PLAN_DRY_RUN = 16
 
 
 class JetB200Error(RuntimeError):
@@ -105,11 +106,14 @@ class OpInfo(C.Structure):
         ("log_tile", C.c_int32),
         ("launches", C.c_int32),
         ("n_stages", C.c_int32),
-        ("pad", C.c_int32),
+        ("gemm_kind", C.c_int32),
         ("flops", C.c_double),
         ("bytes", C.c_double),
         ("step_bytes", C.c_double),
     ]
+
+
+GEMM_KIND_NAMES = {0: "GemmKernel", 1: "SmallMnKernel", 2: "GemmTf32x3Kernel", 3: "GemmDmmaKernel"}
 
 
 class ChainDesc(C.Structure):

@@ -807,6 +807,15 @@ bool ChainFusionEnabled()
     return enabled;
 }
 
+bool ChainTilePaddingEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_CHAIN_NO_PAD");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
+}
+
 bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left)
 {
     // the chained tensor is the larger operand; the other one must be gate-sized
@@ -930,6 +939,22 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
         if (!PlanChain(spec, max_tile_bits, wide, &lay, why, 0, false) &&
             !PlanChain(spec, max_tile_bits, wide - 1, &lay, why, 0, false))
             return 1;
+    }
+    // Short chains touch few bits and would get tiny tiles (2^8 elements: per-tile hand-off latency dominates,
+    // measured 0.3 TB/s on a rank-28 tensor).  Pad the tile with untouched bits up to the largest tile that
+    // still leaves every SM a few tiles.
+    if (ChainTilePaddingEnabled()) {
+        const int log_x = static_cast<int>(spec.x0_bits.size());
+        const int want = std::min(max_tile_bits, std::max(0, log_x - 9));
+        for (int pad = want - lay.params.log_tile; pad > 0; pad--) {
+            ChainLayout bigger;
+            std::string w2;
+            if (PlanChain(spec, max_tile_bits, wide, &bigger, &w2, pad, reg_stages) && bigger.params.log_tile <= want &&
+                bigger.params.log_tile > lay.params.log_tile) {
+                lay = bigger;
+                break;
+            }
+        }
     }
     {
         const size_t smem =

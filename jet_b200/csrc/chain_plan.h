@@ -221,13 +221,25 @@ inline bool PlanChain(const ChainSpec &spec, int max_tile_bits, int lane_bits, C
     for (size_t q = 0; q < x0.size() && static_cast<int>(quiet.size()) < bank_bits; q++)
         if (!touched.count(x0[q]))
             quiet.insert(x0[q]);
-    // padding: more untouched bits (lowest X_0 address bits first) make the tile larger, so that every
-    // compute thread owns a register tile in every stage
-    for (size_t q = 0; q < x0.size() && extra_quiet > 0; q++)
-        if (!touched.count(x0[q]) && !quiet.count(x0[q])) {
-            quiet.insert(x0[q]);
-            extra_quiet--;
+    // padding: more untouched bits make the tile larger — short chains touch few bits, and a tile of 2^8
+    // elements is all hand-off latency (load -> compute -> store barriers per 2 KB).  The lowest untouched
+    // address bits of X_0 and of X_k are taken alternately, so that both the load and the store walk
+    // longer contiguous runs.
+    {
+        size_t q0 = 0, qk = 0;
+        bool from_x0 = true;
+        while (extra_quiet > 0 && (q0 < x0.size() || qk < xk.size())) {
+            const std::vector<int> &src = from_x0 ? x0 : xk;
+            size_t &q = from_x0 ? q0 : qk;
+            while (q < src.size() && (touched.count(src[q]) || quiet.count(src[q])))
+                q++;
+            if (q < src.size()) {
+                quiet.insert(src[q]);
+                extra_quiet--;
+            }
+            from_x0 = !from_x0;
         }
+    }
 
     // physical tile positions
     std::map<int, int> pos;

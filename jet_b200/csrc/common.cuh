@@ -100,6 +100,8 @@ struct ContractPlan {
     std::vector<int32_t> modes_a, modes_b, modes_c;
     int64_t m = 1, n = 1, k = 1;
     int kernel = 0; // 0 = stream, 1 = ttgt
+    // ttgt: which GEMM kernel LaunchGemm will pick for this shape (JB_GEMM_*: what actually launches)
+    int gemm_kind = 0;
     size_t ws_bytes = 0;
     // ttgt
     bool permute_a = false, permute_b = false;
@@ -123,6 +125,8 @@ struct ContractPlan {
     }
 };
 
+// The kernel LaunchGemm dispatches (dtype, m, n, k) to when the plan's workspace is provided: JB_GEMM_* codes.
+int GemmKind(int dtype, int64_t m, int64_t n, int64_t k);
 int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
                      int rank_b, const int64_t *extent_b, const int32_t *modes_b,
                      ContractPlan *plan);
@@ -154,6 +158,7 @@ struct ChainOp {
 };
 
 int ChainMaxTileBits(int dtype);
+bool ChainTilePaddingEnabled(); // false when JB_CHAIN_NO_PAD=1: short chains keep their minimal tiles
 bool ChainFusionEnabled(); // false when JB_DISABLE_CHAIN=1 is set in the environment
 bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left);
 // returns non-zero (reason in *why) when the chain does not fit one tile; not an error

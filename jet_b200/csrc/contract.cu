@@ -614,6 +614,18 @@ size_t GemmWorkspaceBytes(int dtype, int64_t m, int64_t n, int64_t k)
     return ElemBytes(dtype) * static_cast<size_t>(cfg.splits) * m * n;
 }
 
+int GemmKind(int dtype, int64_t m, int64_t n, int64_t k)
+{
+    // the same order as LaunchGemm below
+    if (SmallMnEligible(m, n, k))
+        return JB_GEMM_SMALL_MN;
+    if (TcEnabled() && GemmTcEligible(dtype, m, n, k))
+        return JB_GEMM_TCGEN05;
+    if (DmmaEnabled() && GemmDmmaEligible(dtype, m, n, k))
+        return JB_GEMM_DMMA;
+    return JB_GEMM_FMA;
+}
+
 int LaunchGemm(int dtype, int64_t m, int64_t n, int64_t k, const void *a, const void *b, void *c,
                void *ws, size_t ws_bytes, cudaStream_t stream)
 {
@@ -909,6 +921,7 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
         off += align(eb * static_cast<size_t>(size_b));
         P.launches++;
     }
+    P.gemm_kind = P.gather_a ? JB_GEMM_DMMA : (P.swap_roles ? GemmKind(dtype, P.n, P.m, P.k) : GemmKind(dtype, P.m, P.n, P.k));
     P.ws_gemm_off = off;
     P.ws_gemm_bytes = P.swap_roles ? GemmWorkspaceBytes(dtype, P.n, P.m, P.k) : GemmWorkspaceBytes(dtype, P.m, P.n, P.k);
     if (P.ws_gemm_bytes > 0)

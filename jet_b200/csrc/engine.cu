@@ -403,6 +403,7 @@ int EnsureGraph(jb_plan *p)
 
 int RunSlices(jb_plan *p, long long first, long long list_pos, long long count)
 {
+    JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     JB_TRY(RunShared(p));
     JB_TRY(EnsureGraph(p));
@@ -472,7 +473,9 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     JB_REQUIRE(d != nullptr && out != nullptr, "plan: null argument");
     JB_REQUIRE(d->dtype == JB_C64 || d->dtype == JB_C128, "plan: unknown dtype");
     JB_REQUIRE(d->num_leaves >= 1, "An empty tensor network cannot be contracted.");
-    JB_CUDA(cudaSetDevice(d->device));
+    const bool dry = (d->flags & JB_PLAN_DRY_RUN) != 0; // host-side planning only: no device is touched
+    if (!dry)
+        JB_CUDA(cudaSetDevice(d->device));
     // every early return below releases what the plan holds by then (constant-bank slot, stream, events,
     // pinned buffers, arena): jb_plan_destroy tolerates partially initialised plans
     struct PlanDeleter {
@@ -952,9 +955,10 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     }
     S.arena_bytes = p->arena_bytes;
 
-    JB_TRY(AllocDeviceResources(p));
-    if (d->h_data != nullptr) {
-        JB_TRY(jb_plan_upload(p, d->h_data));
+    if (!dry) {
+        JB_TRY(AllocDeviceResources(p));
+        if (d->h_data != nullptr)
+            JB_TRY(jb_plan_upload(p, d->h_data));
     }
     *out = up.release();
     return 0;
@@ -1012,6 +1016,12 @@ int jb_plan_destroy(jb_plan *p)
 {
     if (p == nullptr)
         return 0;
+    if (p->arena == nullptr && p->stream == nullptr) { // dry run / failed before any device resource
+        if (p->chain_slot >= 0)
+            ChainReleaseSlot(p->device, p->chain_slot);
+        delete p;
+        return 0;
+    }
     cudaSetDevice(p->device);
     if (p->stream)
         cudaStreamSynchronize(p->stream);
@@ -1056,6 +1066,7 @@ int jb_plan_stats(const jb_plan *p, jb_plan_stats_t *stats)
 int jb_plan_upload(jb_plan *p, const void *const *h_data)
 {
     JB_REQUIRE(p && h_data, "plan: null argument");
+    JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     if (p->h_stage != nullptr)
         JB_CUDA(cudaEventSynchronize(p->ev_stage)); // the previous upload has left the pinned mirror
@@ -1080,6 +1091,7 @@ int jb_plan_upload(jb_plan *p, const void *const *h_data)
 int jb_plan_reset(jb_plan *p)
 {
     JB_REQUIRE(p, "plan: null argument");
+    JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     JB_CUDA(cudaMemsetAsync(p->arena + p->acc_off, 0, sizeof(double2) * p->result_elems, p->stream));
     SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), 0, -1, 1);
@@ -1121,6 +1133,7 @@ int jb_plan_run_list(jb_plan *p, const int64_t *ids, int64_t count)
 int jb_plan_sync(jb_plan *p)
 {
     JB_REQUIRE(p, "plan: null argument");
+    JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     JB_CUDA(cudaStreamSynchronize(p->stream));
     return 0;
@@ -1129,6 +1142,7 @@ int jb_plan_sync(jb_plan *p)
 int jb_plan_result(jb_plan *p, double *h_out)
 {
     JB_REQUIRE(p && h_out, "plan: null argument");
+    JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     JB_CUDA(cudaMemcpyAsync(h_out, p->arena + p->acc_off, sizeof(double2) * p->result_elems,
                             cudaMemcpyDeviceToHost, p->stream));
@@ -1251,7 +1265,7 @@ int jb_plan_ops(const jb_plan *p, jb_op_info_t *ops, int32_t cap, int32_t *count
         o.last_step = op.steps.back();
         o.log_tile = op.kernel == 2 ? op.chain.log_tile : 0;
         o.n_stages = op.kernel == 2 ? op.chain.n_stages : 0;
-        o.pad = 0;
+        o.gemm_kind = op.kernel == 1 ? p->steps[op.steps[0]].cp.gemm_kind : 0;
         o.flops = o.bytes = o.step_bytes = 0.0;
         if (op.kernel == 2) {
             o.launches = op.chain.launches;
@@ -1273,6 +1287,7 @@ int jb_plan_profile_ops(jb_plan *p, int64_t slice, int reps, float *ms, int32_t 
 {
     JB_REQUIRE(p && ms, "plan: null argument");
     JB_REQUIRE(slice >= 0 && slice < p->num_slices, "plan: slice id out of bounds");
+    JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     JB_TRY(RunShared(p));
     for (int32_t i = 0; i < cap; i++)

@@ -1,4 +1,7 @@
-"""Seeded greedy contraction-path search (host-side bookkeeping, no tensor data).
+"""Contraction-path search (host-side bookkeeping, no tensor data): `optimize` drives the native optimiser
+(jet_b200/cpp/pathopt.cpp: recursive bisection + subtree reconfiguration + slicing-aware search, the recipe of
+the cotengra runs the reference's benchmarks were prepared with); `greedy_path` / `search` are the seeded greedy
+finder of round 1, kept for small networks and as a fallback for non-power-of-two extents.
 
 Replaces, for the purpose of synthesising inputs, the reference's random-sampling path finder
 (reference python/jet/interpreter.py:533-618) and the offline cotengra search its benchmarks used
@@ -12,7 +15,47 @@ from __future__ import annotations
 import heapq
 import math
 import random
-from typing import Dict, List, Sequence, Tuple
+import json
+import os
+import subprocess
+import tempfile
+from typing import Dict, List, Optional, Sequence, Tuple
+
+PATHOPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "pathopt")
+
+
+def optimize(leaf_indices: Sequence[Sequence[str]], dims: Dict[str, int], target_log2: int = 30, max_slices_log2: int = 40,
+             trials: int = 16, seconds: float = 60.0, threads: int = 8, seed: int = 1, k: int = 10,
+             fixed_slices: Sequence[str] = ()) -> dict:
+    """Path + sliced indices for a network whose extents are powers of two.  Returns the optimiser's report:
+    {"path": [[a, b], ...], "sliced": [names], "log2_slices", "log2_peak_per_slice", "jet_flops_per_slice",
+    "jet_flops_total", "log2_peak_unsliced", "jet_flops_unsliced", ...} (Jet convention: 2*M*N*K per step,
+    reference include/jet/PathInfo.hpp:157-183)."""
+    if not os.path.exists(PATHOPT):
+        raise RuntimeError(f"{PATHOPT} is missing: build it with `make -C jet_b200/cpp pathopt`")
+    number: Dict[str, int] = {}
+    for idx in leaf_indices:
+        for i in idx:
+            number.setdefault(i, len(number))
+    order = sorted(number, key=number.get)
+    lines = [f"{len(leaf_indices)} {len(order)}"] + [f"{name} {int(dims[name])}" for name in order]
+    lines += [" ".join([str(len(idx))] + [str(number[i]) for i in idx]) for idx in leaf_indices]
+    with tempfile.NamedTemporaryFile("w", suffix=".net", delete=False) as f:
+        f.write("\n".join(lines) + "\n")
+        name = f.name
+    try:
+        cmd = [PATHOPT, name, "--target", str(target_log2), "--max-slices", str(max_slices_log2), "--trials", str(trials),
+               "--seconds", str(seconds), "--threads", str(threads), "--seed", str(seed), "--k", str(k)]
+        for s in fixed_slices:
+            cmd += ["--slice", s]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"pathopt failed: {p.stderr.strip()}")
+        out = json.loads(p.stdout)
+    finally:
+        os.unlink(name)
+    out["path"] = [(int(a), int(b)) for a, b in out["path"]]
+    return out
 
 
 def greedy_path(leaf_indices: Sequence[Sequence[str]], dims: Dict[str, int], seed: int = 0, temperature: float = 0.0,

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._lib import (JB_PLAN_KEEP_INTERMEDIATES, JB_PLAN_NO_FUSE, JB_PLAN_NO_GRAPH, JB_PLAN_STORE_RESULTS, NetworkDesc,
+from ._lib import (JB_PLAN_DRY_RUN, JB_PLAN_KEEP_INTERMEDIATES, JB_PLAN_NO_FUSE, JB_PLAN_NO_GRAPH, JB_PLAN_STORE_RESULTS, NetworkDesc,
                    OpInfo, PlanStats, StepInfo, check, lib)
 from .ops import dtype_code
 
@@ -86,7 +86,7 @@ class ContractionPlan:
 
     def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), device: int = 0, keep_intermediates=False,
                  use_graph=True, store_results=False, path: Optional[Sequence[Sequence[int]]] = None,
-                 fuse=True):
+                 fuse=True, dry_run=False):
         self.net = net
         self.sliced = list(sliced)
         self.device = device
@@ -114,7 +114,8 @@ class ContractionPlan:
         self._path = (C.c_int32 * max(len(flat_path), 1))(*flat_path)
         self._sliced = (C.c_int32 * max(len(self.sliced), 1))(*[labels[s] for s in self.sliced])
         flags = (JB_PLAN_KEEP_INTERMEDIATES if keep_intermediates else 0) | (0 if use_graph else JB_PLAN_NO_GRAPH) | (
-            JB_PLAN_STORE_RESULTS if store_results else 0) | (0 if fuse else JB_PLAN_NO_FUSE)
+            JB_PLAN_STORE_RESULTS if store_results else 0) | (0 if fuse else JB_PLAN_NO_FUSE) | (
+            JB_PLAN_DRY_RUN if dry_run else 0)
         desc = NetworkDesc(dtype_code(self.dtype), device, n, self._rank, self._extent, self._mode, self._data,
                            len(steps), self._path, len(self.sliced), self._sliced, flags)
         self._h = C.c_void_p()

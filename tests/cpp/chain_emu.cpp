@@ -43,6 +43,10 @@ int ConflictDegree(const std::vector<unsigned> &addr_by_lane, int elem_bytes)
 }
 } // namespace
 
+static int g_extra_quiet = 0;
+// tile padding with untouched bits (what MakeChainOp asks for on short chains): applies to later runs
+extern "C" void chain_emu_set_extra_quiet(int n) { g_extra_quiet = n; }
+
 extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, int n_steps,
                              const int *r_nbits, const int *r_bits, const int *x_is_left,
                              int max_tile_bits, int lane_bits, const double *x0,
@@ -62,7 +66,7 @@ extern "C" int chain_emu_run(int elem_bytes, int n_x0_bits, const int *x0_bits, 
     }
     ChainLayout lay;
     std::string why;
-    if (!PlanChain(spec, max_tile_bits, lane_bits, &lay, &why)) {
+    if (!PlanChain(spec, max_tile_bits, lane_bits, &lay, &why, g_extra_quiet)) {
         std::fprintf(stderr, "chain_emu: %s\n", why.c_str());
         return 1;
     }

@@ -154,3 +154,38 @@ def test_gate_like_chain_is_conflict_free(emu):
     np.testing.assert_allclose(got, want.reshape(-1), rtol=1e-10, atol=1e-10)
     assert stats[0] <= 13 and stats[2] == 0
     assert stats[1] == 1 and stats[3] == 1 and stats[4] == 1 and stats[5] == 1, stats
+
+
+@pytest.mark.parametrize("elem_bytes", [8, 16])
+def test_padded_tiles_match_stepwise_contraction(emu, elem_bytes):
+    """Short chains get their tile padded with untouched bits (MakeChainOp, jet_b200/csrc/chain.cu: a 2^8 tile is
+    all hand-off latency): same results, same hazard-freedom, for every amount of padding."""
+    rng = np.random.default_rng(99 + elem_bytes)
+    planned = 0
+    try:
+        for trial in range(80):
+            n_bits = int(rng.integers(8, 17))
+            n_steps = int(rng.integers(1, 4))
+            x0_bits, steps = random_chain(rng, n_bits, n_steps, max_k=2, max_n=2)
+            x0 = rng.standard_normal((2,) * n_bits) + 1j * rng.standard_normal((2,) * n_bits)
+            rs = [rng.standard_normal((2,) * len(rb)) + 1j * rng.standard_normal((2,) * len(rb)) if rb
+                  else np.array(rng.standard_normal() + 1j * rng.standard_normal()) for rb, _ in steps]
+            want, wb = x0, list(x0_bits)
+            for (rb, left), r in zip(steps, rs):
+                want, wb = contract_bits(want, wb, r, list(rb), left)
+            emu.chain_emu_set_extra_quiet(0)
+            base = run_emu(emu, x0_bits, steps, x0, rs, elem_bytes=elem_bytes, lane_bits=5)
+            if base is None:
+                continue
+            emu.chain_emu_set_extra_quiet(int(rng.integers(1, 7)))
+            res = run_emu(emu, x0_bits, steps, x0, rs, elem_bytes=elem_bytes, lane_bits=5)
+            if res is None:
+                continue  # the padded tile exceeds the limit: MakeChainOp then tries less padding
+            got, gb, stats = res
+            planned += 1
+            assert gb == wb and stats[2] == 0
+            assert stats[0] >= base[2][0]  # the padded tile is at least as large
+            np.testing.assert_allclose(got, np.asarray(want).reshape(-1), rtol=1e-10, atol=1e-10)
+    finally:
+        emu.chain_emu_set_extra_quiet(0)
+    assert planned >= 40

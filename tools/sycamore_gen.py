@@ -59,10 +59,57 @@ def lattice(rows, cols, removed=None):
     return sites, couplers
 
 
-def circuit(rows, cols, removed, cycles, seed):
+# The 54-qubit Sycamore grid as rows of a square lattice (a diamond-shaped patch; '-' = no qubit), written down
+# from the published device layout; one qubit is removed for the 53-qubit processor (which one is a documented
+# choice here: (3, 2), a boundary site).
+SYCAMORE_GRID = """
+-----AB---
+----ABCD--
+---ABCDEF-
+--ABCDEFGH
+-ABCDEFGHI
+ABCDEFGHI-
+-CDEFGHI--
+--EFGHI---
+---GHI----
+----I-----
+"""
+
+
+def lattice_sycamore(removed=(3, 2)):
+    """Square-lattice sites of the Sycamore patch and the four staggered coupler classes of the supremacy
+    sequence: A / B = the two halves of the vertical couplers (r, c)-(r+1, c), C / D = the two halves of the
+    horizontal couplers (r, c)-(r, c+1); a coupler belongs to the half fixed by the parity of its position in a
+    2 x 2 unit cell, shifted by one on every other line ("staggered": the half-grid pattern whose cycles
+    ABCDCDAB do not factor into independent stripes)."""
+    rows = [ln for ln in SYCAMORE_GRID.strip("\n").split("\n")]
+    sites = [(r, c) for r, ln in enumerate(rows) for c, ch in enumerate(ln) if ch != "-" and (r, c) != removed]
+    have = set(sites)
+
+    def in_layer(a, b, col_offset, vertical):
+        if vertical:  # transpose so that the pair lies along a row
+            a, b = (a[1], a[0]), (b[1], b[0])
+        a, b = sorted((a, b))
+        if a[0] != b[0] or b[1] != a[1] + 1:
+            return False
+        pos = (a[0] % 2, (a[1] - col_offset) % 2)
+        return pos == (0, 0) or pos == (1, 1)
+
+    layers = {"A": (0, True), "B": (1, True), "C": (1, False), "D": (0, False)}
+    couplers = {c: [] for c in "ABCD"}
+    for (r, c) in sites:
+        for other in ((r + 1, c), (r, c + 1)):
+            if other in have:
+                for name, (off, vert) in layers.items():
+                    if in_layer((r, c), other, off, vert):
+                        couplers[name].append(((r, c), other))
+    return sites, couplers
+
+
+def circuit(rows, cols, removed, cycles, seed, layout="brick"):
     """List of ("1q", site, name) / ("fsim", site_u, site_v) in time order."""
     rng = np.random.default_rng(seed)
-    sites, couplers = lattice(rows, cols, removed)
+    sites, couplers = lattice_sycamore(removed if removed is not None else (3, 2)) if layout == "sycamore" else lattice(rows, cols, removed)
     names = sorted(GATES_1Q)
     last = {}
     ops = []
@@ -174,25 +221,38 @@ def network_json(leaves, path, dtype=np.complex64):
     return json.dumps(out, separators=(",", ":"))
 
 
-def build(rows, cols, removed, cycles, seed, trials=8, target_log2=28, bits=None, max_sliced=62):
-    from jet_b200.pathfinder import path_cost, search
+def build(rows, cols, removed, cycles, seed, trials=8, target_log2=28, bits=None, max_sliced=62, layout="brick",
+          optimizer="greedy", seconds=60.0, k=10):
+    """Circuit -> network -> path + sliced indices.  optimizer = "greedy" (round-1 seeded greedy finder + greedy
+    slicer) or "pathopt" (jet_b200/cpp/pathopt.cpp: bisection + subtree reconfiguration + slicing-aware search)."""
+    from jet_b200.pathfinder import optimize, path_cost, search
     from jet_b200.slicing import find_slices
-    sites, ops = circuit(rows, cols, removed, cycles, seed)
+    sites, ops = circuit(rows, cols, removed, cycles, seed, layout)
     if bits is None:
         bits = np.random.default_rng(seed + 12345).integers(0, 2, len(sites)).tolist()
     leaves = to_network(sites, ops, bits)
     leaf_idx = [idx for _, idx, _ in leaves]
     dims = {i: 2 for idx in leaf_idx for i in idx}
-    path, (peak, flops) = search(leaf_idx, dims, trials=trials, seed=seed)
-    sliced = []
-    if peak > target_log2:
-        sliced = find_slices(leaf_idx, dims, path, [], max_elems=2 ** target_log2)
-        if len(sliced) > max_sliced:
-            sliced = sliced[:max_sliced]
+    extra = {}
+    if optimizer == "pathopt":
+        rep = optimize(leaf_idx, dims, target_log2=target_log2, max_slices_log2=max_sliced, trials=trials, seconds=seconds,
+                       seed=seed, k=k)
+        path, sliced = rep["path"], rep["sliced"]
+        peak, flops = rep["log2_peak_unsliced"], rep["jet_flops_unsliced"]
+        extra = dict(optimizer="pathopt", jet_flops_total=rep["jet_flops_total"], search_seconds=rep["seconds"],
+                     search_trials=rep["trials"])
+    else:
+        path, (peak, flops) = search(leaf_idx, dims, trials=trials, seed=seed)
+        sliced = []
+        if peak > target_log2:
+            sliced = find_slices(leaf_idx, dims, path, [], max_elems=2 ** target_log2)
+            if len(sliced) > max_sliced:
+                sliced = sliced[:max_sliced]
     peak_s, flops_s = path_cost(leaf_idx, dims, path, sliced)
-    meta = dict(rows=rows, cols=cols, removed=removed, cycles=cycles, seed=seed, qubits=len(sites), bits=bits,
+    meta = dict(rows=rows, cols=cols, removed=removed, cycles=cycles, seed=seed, layout=layout, qubits=len(sites), bits=bits,
                 leaves=len(leaves), steps=len(path), log2_peak_unsliced=peak, jet_flops_unsliced=flops,
-                sliced_indices=sliced, log2_num_slices=len(sliced), log2_peak_per_slice=peak_s, jet_flops_per_slice=flops_s)
+                sliced_indices=sliced, log2_num_slices=len(sliced), log2_peak_per_slice=peak_s, jet_flops_per_slice=flops_s,
+                **extra)
     return sites, ops, bits, leaves, path, meta
 
 
@@ -205,10 +265,19 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--trials", type=int, default=8)
     ap.add_argument("--target-log2", type=int, default=28)
+    ap.add_argument("--layout", default="brick", choices=["brick", "sycamore"],
+                    help="brick: rows x cols rotated lattice (round 1); sycamore: the 54-site Sycamore patch with the "
+                         "staggered half-grid coupler classes (--remove picks the missing qubit, default 3,2)")
+    ap.add_argument("--optimizer", default="greedy", choices=["greedy", "pathopt"])
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--max-sliced", type=int, default=62)
     ap.add_argument("--out", default=os.path.join(ROOT, "data", "syc53_m20.json"))
     args = ap.parse_args()
     removed = tuple(int(v) for v in args.remove.split(",")) if args.remove else None
-    _, _, _, leaves, path, meta = build(args.rows, args.cols, removed, args.cycles, args.seed, args.trials, args.target_log2)
+    _, _, _, leaves, path, meta = build(args.rows, args.cols, removed, args.cycles, args.seed, args.trials, args.target_log2,
+                                        max_sliced=args.max_sliced, layout=args.layout, optimizer=args.optimizer,
+                                        seconds=args.seconds, k=args.k)
     with open(args.out, "w") as f:
         f.write(network_json(leaves, path))
     json.dump(meta, open(args.out + ".meta.json", "w"), indent=1)
