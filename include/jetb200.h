@@ -344,6 +344,18 @@ int jb_reduce_sum(jb_comm *comm, void *d_buf, int64_t n_doubles, int root, void 
  * set's first device; afterwards jb_multi_result returns the reduced sum on `root`. */
 int jb_multi_reduce(jb_multi *multi, jb_comm *comm, int root);
 
+
+/* ---- peak probes: roofline denominators measured on the device the caller is on ------------------------------
+ * No reference counterpart (SURVEY 8(d) asks for FP64 / FP32 / TF32 peaks next to the HBM copy bandwidth).
+ * value = TFLOP/s of a dependency-free register-only instruction stream on every SM (kinds 0-3) or GB/s of a
+ * 1 GiB device copy, read + write (kind 4); best of three timed launches, CUDA events. */
+#define JB_PEAK_FP32_FMA 0      /* fma.rn.f32x2 (FFMA2): what the chain / stream kernels issue */
+#define JB_PEAK_FP64_FMA 1      /* fma.rn.f64 */
+#define JB_PEAK_FP64_DMMA 2     /* mma.sync.m8n8k4.f64: the FP64 tensor pipe of GemmDmmaKernel */
+#define JB_PEAK_TF32_MMA_SYNC 3 /* mma.sync.m16n8k8.tf32: the legacy warp-level tensor path (not tcgen05) */
+#define JB_PEAK_HBM_COPY 4
+int jb_probe_peak(int kind, double *value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,3 +171,15 @@ def device_info(device: int = 0) -> dict:
     mi = C.c_int()
     check(lib().jb_device_info(device, C.byref(sm), C.byref(tot), C.byref(l2), C.byref(ma), C.byref(mi)))
     return dict(sm_count=sm.value, total_bytes=tot.value, l2_bytes=l2.value, cc=(ma.value, mi.value))
+
+
+PEAK_KINDS = {"fp32_fma": 0, "fp64_fma": 1, "fp64_dmma": 2, "tf32_mma_sync": 3, "hbm_copy": 4}
+
+
+def probe_peak(kind: str) -> float:
+    """Measured peak of the current device: TFLOP/s (fp32_fma, fp64_fma, fp64_dmma, tf32_mma_sync) or GB/s (hbm_copy)."""
+    import ctypes as _C
+
+    v = _C.c_double()
+    check(lib().jb_probe_peak(PEAK_KINDS[kind], _C.byref(v)))
+    return float(v.value)
