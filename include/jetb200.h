@@ -243,6 +243,9 @@ int jb_plan_slice_result(jb_plan *plan, int64_t ordinal, void *h_out);
 int jb_plan_slice_results(jb_plan *plan, int64_t first_ordinal, int64_t count, void *h_out);
 /* With JB_PLAN_KEEP_INTERMEDIATES: copy node `node`'s tensor (last slice run) to the host. */
 int jb_plan_node(jb_plan *plan, int32_t node, void *h_out, int64_t *elems);
+/* Modes and extents of node `node` as the steps see it (a sliced leaf: after slicing); modes / extent may be NULL,
+ * otherwise they receive up to JB_MAX_RANK entries. */
+int jb_plan_node_info(const jb_plan *plan, int32_t node, int32_t *rank, int32_t *modes, int64_t *extent);
 int jb_plan_sync(jb_plan *plan);
 /* Device time (ms) between the first and last kernel of the most recent jb_plan_run*, measured
  * with CUDA events on the plan's stream. */

@@ -160,7 +160,7 @@ SYMBOLS = [
     "jb_multi_create", "jb_multi_destroy", "jb_multi_stats", "jb_multi_num_plans", "jb_multi_plan", "jb_multi_upload",
     "jb_multi_reset", "jb_multi_run", "jb_multi_run_list", "jb_multi_sync", "jb_multi_result",
     "jb_multi_slice_result", "jb_multi_slice_results", "jb_multi_last_ms", "jb_comm_unique_id", "jb_comm_create",
-    "jb_comm_destroy", "jb_comm_info", "jb_reduce_sum", "jb_multi_reduce", "jb_probe_peak",
+    "jb_comm_destroy", "jb_comm_info", "jb_reduce_sum", "jb_multi_reduce", "jb_probe_peak", "jb_plan_node_info",
 ]
 
 _lib = None
@@ -258,6 +258,7 @@ def lib():
         L.jb_reduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         L.jb_multi_reduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.jb_probe_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.jb_plan_node_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

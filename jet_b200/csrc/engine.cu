@@ -1196,6 +1196,21 @@ int jb_plan_node(jb_plan *p, int32_t node, void *h_out, int64_t *elems)
     return 0;
 }
 
+int jb_plan_node_info(const jb_plan *p, int32_t node, int32_t *rank, int32_t *modes, int64_t *extent)
+{
+    JB_REQUIRE(p && rank, "plan: null argument");
+    JB_REQUIRE(node >= 0 && node < static_cast<int>(p->nodes.size()), "plan: node out of range");
+    const Node &n = p->nodes[node];
+    *rank = static_cast<int32_t>(n.modes.size());
+    for (size_t j = 0; j < n.modes.size(); j++) {
+        if (modes)
+            modes[j] = n.modes[j];
+        if (extent)
+            extent[j] = n.extent[j];
+    }
+    return 0;
+}
+
 int jb_plan_last_ms(jb_plan *p, float *ms)
 {
     JB_REQUIRE(p && ms, "plan: null argument");

@@ -191,6 +191,19 @@ class ContractionPlan:
         check(lib().jb_plan_node(self._h, node, out.ctypes.data_as(C.c_void_p), C.byref(n)))
         return out
 
+    def node_modes(self, node: int) -> List[int]:
+        """Integer mode labels of node `node` as the steps see it (row-major axes, first slowest)."""
+        rank = C.c_int32()
+        modes = (C.c_int32 * 64)()
+        check(lib().jb_plan_node_info(self._h, node, C.byref(rank), modes, None))
+        return [int(modes[i]) for i in range(rank.value)]
+
+    def node_shape(self, node: int) -> List[int]:
+        rank = C.c_int32()
+        ext = (C.c_int64 * 64)()
+        check(lib().jb_plan_node_info(self._h, node, C.byref(rank), None, ext))
+        return [int(ext[i]) for i in range(rank.value)]
+
     def last_ms(self) -> float:
         ms = C.c_float()
         check(lib().jb_plan_last_ms(self._h, C.byref(ms)))

@@ -16,7 +16,8 @@ def test_reference_arm_json_line():
         pytest.skip("oracle/_ref not built")
     if not os.path.exists(os.path.join(ROOT, "data", "_ref", "m12.json")):
         pytest.skip("data/_ref missing")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "sycamore53_m12_s9"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
@@ -37,3 +38,5 @@ def test_bench_workloads_resolve():
     assert len(net.tensors) == 410 and len(net.path) == 409 and len(sliced) == 9 and dt == "complex64"
     net, sliced, dt, _ = bench.load_network("sycamore53_m20_synth")
     assert len(net.tensors) == 870 and len(sliced) == 58
+    net, sliced, dt, _ = bench.load_network("sycamore53_m20")  # the default workload
+    assert len(net.tensors) == 860 and len(sliced) == 22 and dt == "complex64"

@@ -1,34 +1,68 @@
-"""Generate data/<stem>.golden.json (default stem: sycamore53_m20): slices of the synthetic m=20 network contracted by the
-UNMODIFIED reference (oracle/_ref: TaskBasedContractor + deletion tasks) in complex64 and complex128.
-Run in the container that has /root/reference (several minutes per slice and dtype):
-    python tools/make_m20_golden.py [--stem sycamore53_m20] [slice ids ...]
-The complex128 value is the reference's own higher-precision result for the same slice: a single
-slice amplitude is a sum with heavy cancellation, so two correct complex64 engines differ by more
-than 1e-5 on it (the reference's complex64 result is 2e-4 away from its complex128 one on slice 0);
-tests compare against both (SURVEY 8c caveat ii)."""
-import json, os, sys
+"""Generate data/<stem>.golden.json (default stem: sycamore53_m20): slices of the synthetic m=20 network contracted by
+the UNMODIFIED reference (oracle/_ref: TaskBasedContractor + reduction + deletion tasks) in complex64 and complex128.
+
+A slice of the GPU workload holds tensors of 2^30-2^31 elements, which the reference's CPU path cannot hold (one
+std::vector per task, complex128) or takes hours on; so the reference evaluates the SAME number another way: with
+the workload's sliced indices fixed to the slice's digits, jet_b200/cpp/pathopt finds a path and `extra` more
+indices to slice for a small peak (the value of a slice does not depend on the contraction order), and the 2^extra
+sub-slices go through the reference's own sliced flow (jet_sliced.cpp: SliceIndices copies -> AddContractionTasks
+-> AddReductionTask -> Contract); the reduction result IS the slice amplitude — an identity of the contraction,
+not an approximation.  Run in the container that has /root/reference:
+    python tools/make_m20_golden.py [--stem sycamore53_m20] [--peak-log2 24] [slice ids ...]
+The complex128 value is the truth the tests compare against (1e-12 for the complex128 engine; the complex64 engine
+is compared with it at the accuracy the conditioning of the sum allows, see tests/test_m20_synth.py)."""
+import json
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from jet_b200.pathfinder import optimize  # noqa: E402
 from oracle import ref  # noqa: E402
 
 DATA = os.path.join(ROOT, "data")
 argv = sys.argv[1:]
-stem = "sycamore53_m20"
-if argv and argv[0] == "--stem":
-    stem, argv = argv[1], argv[2:]
-ids = [int(a) for a in argv] or [0, 12345678]
+stem, peak_log2 = "sycamore53_m20", 24
+while argv and argv[0].startswith("--"):
+    if argv[0] == "--stem":
+        stem, argv = argv[1], argv[2:]
+    elif argv[0] == "--peak-log2":
+        peak_log2, argv = int(argv[1]), argv[2:]
+    else:
+        raise SystemExit("unknown option " + argv[0])
+ids = [int(a) for a in argv] or [0, 1234567]
 meta = json.load(open(os.path.join(DATA, stem + ".meta.json")))
 text = open(os.path.join(DATA, stem + ".json")).read()
+js = json.loads(text)
+leaf = [t[1] for t in js["tensors"]]
+dims = {i: d for t in js["tensors"] for i, d in zip(t[1], t[2])}
+path = [tuple(p) for p in js["path"]]
+sliced = list(meta["sliced_indices"])
+rep = optimize(leaf, dims, target_log2=peak_log2, max_slices_log2=60, trials=32, seconds=120, seed=3, k=10,
+               fixed_slices=sliced)
+full = list(rep["sliced"])
+assert full[:len(sliced)] == sliced, "the workload's sliced indices must stay the slowest digits"
+extra = full[len(sliced):]
+n_sub = 1
+for i in extra:
+    n_sub *= dims[i]
+js["path"] = [list(p) for p in rep["path"]]
+text = json.dumps(js, separators=(",", ":"))
+print(f"{stem}: {len(sliced)} sliced indices + {len(extra)} extra {extra} -> {n_sub} sub-slices of peak 2^{rep['log2_peak_per_slice']} "
+      f"elements, {rep['jet_flops_per_slice']:.3g} Jet-flops each ({n_sub * rep['jet_flops_per_slice']:.3g} per slice; the workload's "
+      f"own path: {meta['jet_flops_per_slice']:.3g})", flush=True)
 out_path = os.path.join(DATA, stem + ".golden.json")
 gold = json.load(open(out_path)) if os.path.exists(out_path) else {}
 ref.set_blas_threads(1)
+threads = os.cpu_count() or 1
 for v in ids:
     e = gold.setdefault(str(v), {})
+    e["extra_indices"], e["sub_slices"] = extra, n_sub
     for dt, key in (("complex64", ""), ("complex128", "_c128")):
         if ("re" + key) in e:
             continue
-        r, sec, fl = ref.network(text, dt, meta["sliced_indices"], v, mode=2, threads=8, num_slices=1)
+        r, sec, fl = ref.network(text, dt, full, v * n_sub, mode=2, threads=threads, num_slices=n_sub)
         e["re" + key], e["im" + key] = float(r[0].real), float(r[0].imag)
-        e["jet_flops"], e["ref_seconds_here" + key] = fl, sec
-        print(v, dt, r[0], sec, flush=True)
+        e["jet_flops_reference"], e["ref_seconds_here" + key] = fl, sec
+        print(v, dt, r[0], f"{sec:.1f} s", flush=True)
         json.dump(gold, open(out_path, "w"), indent=1)
