@@ -192,6 +192,8 @@ typedef struct jb_network_desc_t {
     int32_t num_sliced;
     const int32_t *sliced_modes; /* [num_sliced] */
     int32_t flags;               /* JB_PLAN_* */
+    int32_t batch;               /* slices contracted per launch: 0 = automatic (small per-slice tensors only), 1 = off,
+                                    n = at most n (rounded down to a power of two, bounded by memory) */
 } jb_network_desc_t;
 
 #define JB_PLAN_KEEP_INTERMEDIATES 1 /* no buffer reuse: every step output stays readable */
@@ -221,6 +223,8 @@ typedef struct jb_plan_stats_t {
     double jet_flops_per_slice; /* 2*M*N*K over ALL steps: PathInfo::GetTotalFlops convention */
     size_t arena_bytes;        /* device memory reserved */
     int64_t max_step_elems;    /* largest intermediate */
+    int32_t batch;             /* slices contracted per launch (slice batching; 1 = off) */
+    int32_t pad;
 } jb_plan_stats_t;
 
 int jb_plan_create(const jb_network_desc_t *desc, jb_plan **plan);

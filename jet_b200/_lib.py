@@ -52,6 +52,7 @@ class NetworkDesc(C.Structure):
         ("num_sliced", C.c_int32),
         ("sliced_modes", C.POINTER(C.c_int32)),
         ("flags", C.c_int32),
+        ("batch", C.c_int32),
     ]
 
 
@@ -77,6 +78,8 @@ class PlanStats(C.Structure):
         ("jet_flops_per_slice", C.c_double),
         ("arena_bytes", C.c_size_t),
         ("max_step_elems", C.c_int64),
+        ("batch", C.c_int32),
+        ("pad", C.c_int32),
     ]
 
 

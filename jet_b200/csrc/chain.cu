@@ -23,6 +23,9 @@ namespace jb {
 
 struct ChainPtrs {
     const void *r[kChainMaxSteps];
+    // slice batching: blockIdx.y = slice within the batch; byte distance between consecutive slices' tensors
+    long long stride_r[kChainMaxSteps];
+    long long stride_x0, stride_xk;
 };
 
 static_assert(sizeof(ChainParams) + sizeof(ChainPtrs) <= 4000, "kernel parameter space is 4 KB");
@@ -469,6 +472,8 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
                 const __grid_constant__ ChainPtrs rp)
 {
     using C = typename Cplx<R>::type;
+    X0 = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(X0) + blockIdx.y * rp.stride_x0);
+    Xk = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(Xk) + blockIdx.y * rp.stride_xk);
     constexpr int LOGT = ChainCfg<R>::kLogThreads;
     constexpr int GT = 1 << LOGT;                      // threads of one compute group
     constexpr int CT = NG * GT;                        // all compute threads (NG groups, NB tile buffers)
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     // of the steps that run through the generic shared-memory path
     for (int s = 0; s < p.n_steps; s++) {
         const ChainStepParams &q = p.step[s];
-        const C *Rs = static_cast<const C *>(rp.r[s]);
+        const C *Rs = reinterpret_cast<const C *>(static_cast<const unsigned char *>(rp.r[s]) + blockIdx.y * rp.stride_r[s]);
         const int np = q.np;
         const int N = 1 << q.log_n;
         const int total = np << q.log_k;
@@ -740,7 +745,7 @@ bool ChainUseThreeGroups(bool is_c64, int log_tile)
 
 template <typename R>
 int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk, int slot,
-                 cudaStream_t stream)
+                 cudaStream_t stream, int batch)
 {
     using C = typename Cplx<R>::type;
     JB_REQUIRE(slot >= 0 && slot < kChainConstSlots, "chain: no constant-bank slot");
@@ -753,6 +758,10 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     for (int sg = 0; sg < p.n_stages; sg++)
         uses_const = uses_const || p.stage[sg].kind == 1;
     if (uses_const) {
+        // one set of matrices per launch: the slices of a batch must share every small operand
+        for (int st = 0; st < p.n_steps; st++)
+            JB_REQUIRE(batch == 1 || ptrs.stride_r[st] == 0,
+                       "chain: register stages cannot be batched over slice-dependent operands");
         JB_REQUIRE(p.resident_elems <= kChainConstEntries, "chain: too many matrix entries");
         void *sym = nullptr;
         JB_CUDA(cudaGetSymbolAddress(&sym, g_chain_const));
@@ -763,11 +772,13 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     const int buffers = wide ? 5 : 3;
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
-    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(p.n_tiles, NumSMs())));
+    // a batch of slices shares the SMs: each slice gets its share of the persistent CTAs, at least one
+    const int grid = static_cast<int>(
+        std::max<long long>(1, std::min<long long>(p.n_tiles, std::max(1, NumSMs() / batch))));
     auto launch = [&](auto kernel, int threads) -> int {
         if (smem > 48 * 1024)
             JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<grid, threads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p, ptrs);
+        kernel<<<dim3(grid, batch), threads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p, ptrs);
         return 0;
     };
     if constexpr (sizeof(C) == 8) {
@@ -834,7 +845,7 @@ bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left)
 
 int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vector<int64_t> &extent_x,
                 const std::vector<ChainOperand> &ops, int max_tile_bits, ChainOp *out,
-                std::string *why)
+                std::string *why, bool allow_register_stages)
 {
     std::string dummy;
     if (why == nullptr)
@@ -929,7 +940,7 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     ChainLayout lay;
     const int wide = spec.elem_bytes == 8 ? 5 : 4;
     // small tensors are launch-latency bound: no register stages -> no constant-bank upload, one launch
-    bool reg_stages = x0_elems > double(1 << 15);
+    bool reg_stages = allow_register_stages && x0_elems > double(1 << 15);
     if (!PlanChain(spec, max_tile_bits, wide, &lay, why, 0, reg_stages) &&
         !PlanChain(spec, max_tile_bits, wide - 1, &lay, why, 0, reg_stages))
         return 1;
@@ -1029,7 +1040,7 @@ void ChainReleaseSlot(int device, int slot)
 int ChainOperatorSlot() { return kChainConstSlots - 1; }
 
 int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, int slot,
-                cudaStream_t stream)
+                cudaStream_t stream, const ChainBatchArgs *batch)
 {
     ChainParams p;
     JB_REQUIRE(op.blob.size() == sizeof(p), "chain: not planned");
@@ -1038,9 +1049,18 @@ int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *x
     std::memset(&ptrs, 0, sizeof(ptrs));
     for (int s = 0; s < op.n_steps; s++)
         ptrs.r[s] = r[s];
+    int count = 1;
+    if (batch != nullptr && batch->count > 1) {
+        JB_REQUIRE(batch->count <= 65535, "chain: batch out of range");
+        count = batch->count;
+        ptrs.stride_x0 = batch->stride_x0;
+        ptrs.stride_xk = batch->stride_xk;
+        for (int s = 0; s < op.n_steps; s++)
+            ptrs.stride_r[s] = batch->stride_r[s];
+    }
     if (op.dtype == JB_C64)
-        return LaunchChainT<float>(p, ptrs, x0, xk, slot, stream);
-    return LaunchChainT<double>(p, ptrs, x0, xk, slot, stream);
+        return LaunchChainT<float>(p, ptrs, x0, xk, slot, stream, count);
+    return LaunchChainT<double>(p, ptrs, x0, xk, slot, stream, count);
 }
 
 } // namespace jb

@@ -127,11 +127,23 @@ struct ContractPlan {
 
 // The kernel LaunchGemm dispatches (dtype, m, n, k) to when the plan's workspace is provided: JB_GEMM_* codes.
 int GemmKind(int dtype, int64_t m, int64_t n, int64_t k);
+// Slice batching: one launch processes `count` slices whose per-slice tensors lie `stride` bytes apart (operands
+// shared by all slices have stride 0).  count == 1 (or a null pointer) is the plain launch.
+struct BatchArgs {
+    int count = 1;
+    long long stride_a = 0, stride_b = 0, stride_c = 0; // bytes between consecutive slices' A / B / C
+};
+struct ChainBatchArgs {
+    int count = 1;
+    long long stride_x0 = 0, stride_xk = 0;
+    long long stride_r[16] = {0}; // per step: bytes between consecutive slices' small operand (0 = shared)
+};
+
 int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32_t *modes_a,
                      int rank_b, const int64_t *extent_b, const int32_t *modes_b,
                      ContractPlan *plan);
 int LaunchContract(const ContractPlan &plan, const void *a, const void *b, void *c, void *ws,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const BatchArgs *batch = nullptr);
 
 // ---- fused contraction chain (chain.cu) ---------------------------------------------------------
 // A run of ContractTensors calls in which each result is contracted next with a small tensor,
@@ -164,7 +176,7 @@ bool ChainStepEligible(const ContractPlan &cp, bool *x_is_left);
 // returns non-zero (reason in *why) when the chain does not fit one tile; not an error
 int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vector<int64_t> &extent_x,
                 const std::vector<ChainOperand> &ops, int max_tile_bits, ChainOp *out,
-                std::string *why);
+                std::string *why, bool allow_register_stages = true);
 // The step matrices of a chain's register stages live in a constant-bank slot (a gather kernel writes
 // them there before the chain kernel): plans acquire a slot for their lifetime (-1: none free -> no
 // fusion), the operator-level entry points share ChainOperatorSlot().
@@ -172,7 +184,7 @@ int ChainAcquireSlot(int device);
 void ChainReleaseSlot(int device, int slot);
 int ChainOperatorSlot();
 int LaunchChain(const ChainOp &op, const void *x0, const void *const *r, void *xk, int slot,
-                cudaStream_t stream);
+                cudaStream_t stream, const ChainBatchArgs *batch = nullptr);
 
 // ---- elementwise ---------------------------------------------------------------------------------
 int LaunchAdd(int dtype, int64_t n, const void *a, const void *b, void *c, cudaStream_t stream);

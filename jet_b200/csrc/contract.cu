@@ -85,9 +85,14 @@ __global__ void __launch_bounds__(kStreamThreads, (KC * XT * sizeof(R) <= 32 && 
     StreamContractKernel(const typename Cx<R>::type *__restrict__ S,
                          const typename Cx<R>::type *__restrict__ Rsd,
                          typename Cx<R>::type *__restrict__ out,
-                         const __grid_constant__ StreamParams p)
+                         const __grid_constant__ StreamParams p, const long long stride_s, const long long stride_r,
+                         const long long stride_o)
 {
     using C = typename Cx<R>::type;
+    // slice batching: blockIdx.y = slice within the batch; its tensors lie stride_* BYTES further on
+    S = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(S) + blockIdx.y * stride_s);
+    Rsd = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(Rsd) + blockIdx.y * stride_r);
+    out = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(out) + blockIdx.y * stride_o);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *Rm = reinterpret_cast<C *>(smem_raw); // [K][Y]
 
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(kStreamThreads, (KC * XT * sizeof(R) <= 32 && 
 
 template <typename R, int KC, int NR>
 int LaunchStreamT(const StreamParams &p, const void *s, const void *r, void *out,
-                  cudaStream_t stream)
+                  cudaStream_t stream, int batch, long long stride_s, long long stride_r, long long stride_o)
 {
     using C = typename Cx<R>::type;
     constexpr int XT = sizeof(R) == 4 ? 2 : 1;
@@ -209,40 +214,41 @@ int LaunchStreamT(const StreamParams &p, const void *s, const void *r, void *out
     }
     const long long resident =
         static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kStreamThreads, smem);
-    const int grid = static_cast<int>(std::min<long long>(tiles, resident));
-    kernel<<<grid, kStreamThreads, smem, stream>>>(static_cast<const C *>(s),
-                                                   static_cast<const C *>(r),
-                                                   static_cast<C *>(out), p);
+    // a batch of slices shares the resident CTAs: each slice gets its share, at least one CTA
+    const int grid = static_cast<int>(std::min<long long>(tiles, std::max<long long>(1, resident / batch)));
+    kernel<<<dim3(grid, batch), kStreamThreads, smem, stream>>>(static_cast<const C *>(s), static_cast<const C *>(r),
+                                                                static_cast<C *>(out), p, stride_s, stride_r, stride_o);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <typename R, int KC>
 int LaunchStreamK(const StreamParams &p, const void *s, const void *r, void *out,
-                  cudaStream_t stream)
+                  cudaStream_t stream, int batch, long long ss, long long sr, long long so)
 {
     const int y = 1 << p.log_y;
     if (y >= 8)
-        return LaunchStreamT<R, KC, 8>(p, s, r, out, stream);
+        return LaunchStreamT<R, KC, 8>(p, s, r, out, stream, batch, ss, sr, so);
     if (y == 4)
-        return LaunchStreamT<R, KC, 4>(p, s, r, out, stream);
+        return LaunchStreamT<R, KC, 4>(p, s, r, out, stream, batch, ss, sr, so);
     if (y == 2)
-        return LaunchStreamT<R, KC, 2>(p, s, r, out, stream);
-    return LaunchStreamT<R, KC, 1>(p, s, r, out, stream);
+        return LaunchStreamT<R, KC, 2>(p, s, r, out, stream, batch, ss, sr, so);
+    return LaunchStreamT<R, KC, 1>(p, s, r, out, stream, batch, ss, sr, so);
 }
 
 template <typename R>
 int LaunchStream(const StreamParams &p, const void *s, const void *r, void *out,
-                 cudaStream_t stream)
+                 cudaStream_t stream, int batch = 1, long long ss = 0, long long sr = 0, long long so = 0)
 {
+    JB_REQUIRE(batch >= 1 && batch <= 65535, "contract: batch out of range");
     const int k = 1 << p.log_k;
     if (k >= 8)
-        return LaunchStreamK<R, 8>(p, s, r, out, stream);
+        return LaunchStreamK<R, 8>(p, s, r, out, stream, batch, ss, sr, so);
     if (k == 4)
-        return LaunchStreamK<R, 4>(p, s, r, out, stream);
+        return LaunchStreamK<R, 4>(p, s, r, out, stream, batch, ss, sr, so);
     if (k == 2)
-        return LaunchStreamK<R, 2>(p, s, r, out, stream);
-    return LaunchStreamK<R, 1>(p, s, r, out, stream);
+        return LaunchStreamK<R, 2>(p, s, r, out, stream, batch, ss, sr, so);
+    return LaunchStreamK<R, 1>(p, s, r, out, stream, batch, ss, sr, so);
 }
 
 // =================================================================================================
@@ -937,17 +943,31 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
 }
 
 int LaunchContract(const ContractPlan &P, const void *a, const void *b, void *c, void *ws,
-                   cudaStream_t stream)
+                   cudaStream_t stream, const BatchArgs *batch)
 {
+    const int nb = batch ? batch->count : 1;
     if (P.kernel == 0) {
         StreamParams sp;
         std::memcpy(&sp, P.stream_blob.data(), sizeof(sp));
         const bool stream_a = P.stream_blob[sizeof(sp)] != 0;
         const void *s = stream_a ? a : b;
         const void *r = stream_a ? b : a;
+        const long long ss = batch ? (stream_a ? batch->stride_a : batch->stride_b) : 0;
+        const long long sr = batch ? (stream_a ? batch->stride_b : batch->stride_a) : 0;
+        const long long so = batch ? batch->stride_c : 0;
         if (P.dtype == JB_C64)
-            return LaunchStream<float>(sp, s, r, c, stream);
-        return LaunchStream<double>(sp, s, r, c, stream);
+            return LaunchStream<float>(sp, s, r, c, stream, nb, ss, sr, so);
+        return LaunchStream<double>(sp, s, r, c, stream, nb, ss, sr, so);
+    }
+    if (nb > 1) {
+        // TTGT units are not batched: the slices of a batch run one after the other through the one workspace
+        for (int z = 0; z < nb; z++) {
+            const unsigned char *az = static_cast<const unsigned char *>(a) + z * batch->stride_a;
+            const unsigned char *bz = static_cast<const unsigned char *>(b) + z * batch->stride_b;
+            unsigned char *cz = static_cast<unsigned char *>(c) + z * batch->stride_c;
+            JB_TRY(LaunchContract(P, az, bz, cz, ws, stream, nullptr));
+        }
+        return 0;
     }
     JB_REQUIRE(P.ws_bytes == 0 || ws != nullptr, "contract: workspace required");
     unsigned char *w = static_cast<unsigned char *>(ws);

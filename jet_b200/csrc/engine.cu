@@ -110,24 +110,22 @@ struct DeviceState {
     unsigned int pad;
 };
 
-__device__ __forceinline__ long long CurrentSlice(const DeviceState *st, const long long *list)
-{
-    return st->list_pos >= 0 ? list[st->list_pos] : st->next_id;
-}
-
 // grid (chunks of kSliceChunk view elements, descriptors): the chunk index is in grid.x (limit 2^31 - 1) so a
 // view of any size fits; the descriptor count (sliced leaves + deferred roots) stays far below 65535
 template <typename V>
 __global__ void __launch_bounds__(128)
     SliceLeavesKernel(V *__restrict__ arena, const SliceLeafDesc *__restrict__ descs,
-                      const DeviceState *__restrict__ st, const long long *__restrict__ list)
+                      const DeviceState *__restrict__ st, const long long *__restrict__ list,
+                      const long long view_base, const long long view_stride)
 {
     const SliceLeafDesc &d = descs[blockIdx.y];
     const long long e0 = static_cast<long long>(blockIdx.x) * kSliceChunk;
     if (e0 >= d.out_elems)
         return;
     const long long e1 = min(d.out_elems, e0 + kSliceChunk);
-    const long long sid = CurrentSlice(st, list);
+    // slice batching: blockIdx.z = slice within the batch; its views live view_stride elements further on
+    const long long sid = st->list_pos >= 0 ? list[st->list_pos + blockIdx.z] : st->next_id + blockIdx.z;
+    V *__restrict__ views = arena + view_base + blockIdx.z * view_stride;
     long long base = d.src_off;
     for (int s = 0; s < d.n_sl; s++)
         base += ((sid / d.sl_div[s]) % d.sl_dim[s]) * d.sl_stride[s];
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(128)
             long long off = base;
             for (int j = 0; j < d.n_rem; j++)
                 off += ((e >> d.rem_shift[j]) & (d.rem_ext[j] - 1)) * d.rem_stride[j];
-            arena[d.dst_off + e] = arena[off];
+            views[d.dst_off + e] = arena[off];
         }
         return;
     }
@@ -146,27 +144,30 @@ __global__ void __launch_bounds__(128)
             off += (rem % d.rem_ext[j]) * d.rem_stride[j];
             rem /= d.rem_ext[j];
         }
-        arena[d.dst_off + e] = arena[off];
+        views[d.dst_off + e] = arena[off];
     }
 }
 
-// Grid-stride over the result elements; the CTA that finishes last advances the slice cursor (every CTA has
-// read `ordinal` before it counts itself done, so the update cannot race with a reader).
+// Grid-stride over the result elements; the results of the `batch` slices of one launch (result_stride elements
+// apart) are added in slice order; the CTA that finishes last advances the slice cursor (every CTA has read
+// `ordinal` before it counts itself done, so the update cannot race with a reader).
 template <typename C>
 __global__ void __launch_bounds__(256)
     AccumulateKernel(const C *__restrict__ result, double2 *__restrict__ acc, C *__restrict__ store,
-                     long long elems, long long store_cap, DeviceState *st)
+                     long long elems, long long store_cap, DeviceState *st, int batch, long long result_stride)
 {
     const long long ordinal = st->ordinal;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < elems; i += stride) {
-        const C v = result[i];
         double2 a = acc[i];
-        a.x += static_cast<double>(v.x);
-        a.y += static_cast<double>(v.y);
+        for (int z = 0; z < batch; z++) {
+            const C v = result[z * result_stride + i];
+            a.x += static_cast<double>(v.x);
+            a.y += static_cast<double>(v.y);
+            if (store != nullptr && ordinal + z < store_cap)
+                store[(ordinal + z) * elems + i] = v;
+        }
         acc[i] = a;
-        if (store != nullptr && ordinal < store_cap)
-            store[ordinal * elems + i] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -177,11 +178,11 @@ __global__ void __launch_bounds__(256)
         }
         if (last) {
             st->ctas_done = 0;
-            st->ordinal = ordinal + 1;
+            st->ordinal = ordinal + batch;
             if (st->list_pos >= 0)
-                st->list_pos = st->list_pos + 1;
+                st->list_pos = st->list_pos + batch;
             else
-                st->next_id = st->next_id + 1;
+                st->next_id = st->next_id + batch;
         }
     }
 }
@@ -208,6 +209,7 @@ struct Node {
     int desc = -1;         // index of this node's slice descriptor (sliced leaves and deferred roots)
     int last_use = -1;     // last step (in execution order) reading this node
     bool used_by_slice_step = false;
+    bool per_slice = false; // `offset` is relative to the per-slice region (replicated `batch` times)
 };
 
 struct Step {
@@ -253,6 +255,12 @@ struct jb_plan {
     size_t ws_off = 0, ws_bytes = 0;
     size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0;
     int chain_slot = -1; // constant-bank slot of the fused chains (-1: none, fusion off)
+    // slice batching: the per-slice tensors (views, per-slice intermediates) live in a region of slice_bytes that
+    // is replicated `batch` times from slice_base on; one graph replay then contracts `batch` slices
+    int batch = 1;
+    size_t slice_base = 0, slice_bytes = 0;
+    cudaGraph_t graph1 = nullptr; // the single-slice variant (remainders, profiling)
+    cudaGraphExec_t graph_exec1 = nullptr;
     int64_t store_cap = 0, list_cap = 0;
     int64_t result_elems = 1;
     int result_node = -1;
@@ -280,23 +288,46 @@ struct jb_plan {
 
 namespace {
 
-int LaunchOp(jb_plan *p, const Op &op)
+unsigned char *NodePtr(const jb_plan *p, int node)
 {
-    // a deferred root is written unsliced (raw_offset); everything else where its consumers read it
-    const Node &out = p->nodes[op.out];
-    unsigned char *dst = p->arena + (out.is_view ? out.raw_offset : out.offset);
-    if (op.kernel == 2) {
-        const void *r[kChainMaxSteps];
-        for (size_t i = 0; i < op.r_nodes.size(); i++)
-            r[i] = p->arena + p->nodes[op.r_nodes[i]].offset;
-        return LaunchChain(op.chain, p->arena + p->nodes[op.x0].offset, r, dst, p->chain_slot, p->stream);
-    }
-    const Step &st = p->steps[op.steps[0]];
-    return LaunchContract(st.cp, p->arena + p->nodes[st.a].offset, p->arena + p->nodes[st.b].offset, dst,
-                          p->arena + p->ws_off, p->stream);
+    const Node &n = p->nodes[node];
+    return p->arena + (n.per_slice ? p->slice_base : 0) + n.offset;
+}
+long long NodeStride(const jb_plan *p, int node)
+{
+    return p->nodes[node].per_slice ? static_cast<long long>(p->slice_bytes) : 0;
 }
 
-int LaunchSliceViews(jb_plan *p)
+// `batch` slices per launch: per-slice operands lie slice_bytes apart, shared ones have stride 0
+int LaunchOp(jb_plan *p, const Op &op, int batch)
+{
+    // a deferred root is written unsliced (raw_offset, shared region); everything else where its consumers read it
+    const Node &out = p->nodes[op.out];
+    unsigned char *dst = out.is_view ? p->arena + out.raw_offset : NodePtr(p, op.out);
+    const long long dst_stride = out.is_view ? 0 : NodeStride(p, op.out);
+    if (op.kernel == 2) {
+        const void *r[kChainMaxSteps];
+        ChainBatchArgs ba;
+        ba.count = batch;
+        ba.stride_x0 = NodeStride(p, op.x0);
+        ba.stride_xk = dst_stride;
+        for (size_t i = 0; i < op.r_nodes.size(); i++) {
+            r[i] = NodePtr(p, op.r_nodes[i]);
+            ba.stride_r[i] = NodeStride(p, op.r_nodes[i]);
+        }
+        return LaunchChain(op.chain, NodePtr(p, op.x0), r, dst, p->chain_slot, p->stream, batch > 1 ? &ba : nullptr);
+    }
+    const Step &st = p->steps[op.steps[0]];
+    BatchArgs ba;
+    ba.count = batch;
+    ba.stride_a = NodeStride(p, st.a);
+    ba.stride_b = NodeStride(p, st.b);
+    ba.stride_c = dst_stride;
+    return LaunchContract(st.cp, NodePtr(p, st.a), NodePtr(p, st.b), dst, p->arena + p->ws_off, p->stream,
+                          batch > 1 ? &ba : nullptr);
+}
+
+int LaunchSliceViews(jb_plan *p, int batch)
 {
     if (p->slice_descs.empty())
         return 0;
@@ -305,38 +336,40 @@ int LaunchSliceViews(jb_plan *p)
         max_out = std::max(max_out, sd.out_elems);
     JB_REQUIRE(p->slice_descs.size() <= 65535, "plan: more than 65535 sliced leaves");
     const dim3 n(static_cast<unsigned>((max_out + kSliceChunk - 1) / kSliceChunk),
-                 static_cast<unsigned>(p->slice_descs.size()), 1);
+                 static_cast<unsigned>(p->slice_descs.size()), static_cast<unsigned>(batch));
+    const long long base = static_cast<long long>(p->slice_base / p->eb), stride = static_cast<long long>(p->slice_bytes / p->eb);
     if (p->dtype == JB_C64)
         SliceLeavesKernel<uint2><<<n, 128, 0, p->stream>>>(p->At<uint2>(0), p->At<SliceLeafDesc>(p->descs_off),
                                                           p->At<DeviceState>(p->state_off),
-                                                          p->At<long long>(p->list_off));
+                                                          p->At<long long>(p->list_off), base, stride);
     else
         SliceLeavesKernel<uint4><<<n, 128, 0, p->stream>>>(p->At<uint4>(0), p->At<SliceLeafDesc>(p->descs_off),
                                                           p->At<DeviceState>(p->state_off),
-                                                          p->At<long long>(p->list_off));
+                                                          p->At<long long>(p->list_off), base, stride);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
 
-int EnqueueSliceBody(jb_plan *p)
+int EnqueueSliceBody(jb_plan *p, int batch)
 {
-    JB_TRY(LaunchSliceViews(p));
+    JB_TRY(LaunchSliceViews(p, batch));
     for (const Op &op : p->ops)
-        JB_TRY(LaunchOp(p, op));
+        JB_TRY(LaunchOp(p, op, batch));
     const bool store = (p->flags & JB_PLAN_STORE_RESULTS) != 0;
-    const void *res = p->arena + p->nodes[p->result_node].offset;
+    const void *res = NodePtr(p, p->result_node);
+    const long long res_stride = NodeStride(p, p->result_node) / static_cast<long long>(p->eb);
     const unsigned acc_grid = static_cast<unsigned>(
         std::max<long long>(1, std::min<long long>((p->result_elems + 1023) / 1024, 4ll * NumSMs())));
     if (p->dtype == JB_C64)
         AccumulateKernel<float2><<<acc_grid, 256, 0, p->stream>>>(
             static_cast<const float2 *>(res), p->At<double2>(p->acc_off),
             store ? p->At<float2>(p->store_off) : nullptr, p->result_elems, p->store_cap,
-            p->At<DeviceState>(p->state_off));
+            p->At<DeviceState>(p->state_off), batch, res_stride);
     else
         AccumulateKernel<double2><<<acc_grid, 256, 0, p->stream>>>(
             static_cast<const double2 *>(res), p->At<double2>(p->acc_off),
             store ? p->At<double2>(p->store_off) : nullptr, p->result_elems, p->store_cap,
-            p->At<DeviceState>(p->state_off));
+            p->At<DeviceState>(p->state_off), batch, res_stride);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -344,7 +377,7 @@ int EnqueueSliceBody(jb_plan *p)
 int EnqueueShared(jb_plan *p)
 {
     for (const Op &op : p->shared_ops)
-        JB_TRY(LaunchOp(p, op));
+        JB_TRY(LaunchOp(p, op, 1));
     return 0;
 }
 
@@ -382,12 +415,12 @@ int RunShared(jb_plan *p)
     return 0;
 }
 
-int EnsureGraph(jb_plan *p)
+int CaptureBody(jb_plan *p, int batch, cudaGraph_t *graph, cudaGraphExec_t *exec)
 {
-    if (p->graph_exec != nullptr || (p->flags & JB_PLAN_NO_GRAPH))
+    if (*exec != nullptr)
         return 0;
     JB_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = EnqueueSliceBody(p);
+    const int rc = EnqueueSliceBody(p, batch);
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
     if (rc != 0) {
@@ -396,8 +429,8 @@ int EnsureGraph(jb_plan *p)
         return rc;
     }
     JB_CUDA(ce);
-    p->graph = g;
-    JB_CUDA(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
+    *graph = g;
+    JB_CUDA(cudaGraphInstantiate(exec, g, 0));
     return 0;
 }
 
@@ -406,21 +439,33 @@ int RunSlices(jb_plan *p, long long first, long long list_pos, long long count)
     JB_REQUIRE(p->arena != nullptr, "plan: created with JB_PLAN_DRY_RUN (no device resources)");
     JB_CUDA(cudaSetDevice(p->device));
     JB_TRY(RunShared(p));
-    JB_TRY(EnsureGraph(p));
+    const bool use_graph = !(p->flags & JB_PLAN_NO_GRAPH);
+    const long long full = p->batch > 1 ? count / p->batch : 0, rest = count - full * p->batch;
+    if (use_graph && full > 0)
+        JB_TRY(CaptureBody(p, p->batch, &p->graph, &p->graph_exec));
+    if (use_graph && rest > 0)
+        JB_TRY(CaptureBody(p, 1, &p->graph1, &p->graph_exec1));
     SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), first, list_pos, 0);
     JB_CUDA(cudaGetLastError());
     JB_CUDA(cudaEventRecord(p->ev0, p->stream));
-    for (long long i = 0; i < count; i++) {
-        if (p->graph_exec)
+    // whole batches first (one replay contracts `batch` slices), then the remainder slice by slice; the device-side
+    // cursor advances by what each replay consumed
+    for (long long i = 0; i < full; i++) {
+        if (use_graph)
             JB_CUDA(cudaGraphLaunch(p->graph_exec, p->stream));
         else
-            JB_TRY(EnqueueSliceBody(p));
+            JB_TRY(EnqueueSliceBody(p, p->batch));
+    }
+    for (long long i = 0; i < rest; i++) {
+        if (use_graph)
+            JB_CUDA(cudaGraphLaunch(p->graph_exec1, p->stream));
+        else
+            JB_TRY(EnqueueSliceBody(p, 1));
     }
     JB_CUDA(cudaEventRecord(p->ev1, p->stream));
     p->have_run = true;
     return 0;
 }
-
 
 // Everything a plan owns on its device: arena, stream, events, pinned staging.  Shared by jb_plan_create and
 // jb_plan_clone (the host-side plan is computed once and copied).
@@ -611,7 +656,8 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     }
 
     // ---- arena layout: raw leaves, then sliced views ----------------------------------------------
-    OffsetAllocator alloc;
+    OffsetAllocator alloc;  // shared region: raw leaves, slice-independent tensors, fixed regions
+    OffsetAllocator salloc; // per-slice region (replicated `batch` times): views and per-slice intermediates
     for (int i = 0; i < d->num_leaves; i++) {
         Node &n = p->nodes[i];
         n.raw_offset = alloc.Alloc(n.elems * p->eb);
@@ -676,8 +722,9 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         }
         sd.src_off = static_cast<long long>(n.raw_offset / p->eb);
         n.raw_elems = n.elems;
-        n.offset = alloc.Alloc(out_elems * p->eb);
-        sd.dst_off = static_cast<long long>(n.offset / p->eb);
+        n.offset = salloc.Alloc(out_elems * p->eb);
+        n.per_slice = true;
+        sd.dst_off = static_cast<long long>(n.offset / p->eb); // relative to the slice's region
         n.modes = new_modes;
         n.extent = new_ext;
         n.elems = out_elems;
@@ -732,6 +779,13 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     for (size_t s = 0; s < p->steps.size(); s++)
         (p->steps[s].shared ? p->shared_order : p->slice_order).push_back(static_cast<int>(s));
 
+    // ---- slice batching (decided in two steps: candidate here, batch size once the region sizes are known) ----
+    constexpr int64_t kBatchMaxElems = 1 << 20; // per-slice tensors above this fill the GPU on their own
+    int want_batch = d->batch;
+    if (const char *e = getenv("JB_PLAN_BATCH"))
+        want_batch = atoi(e);
+    bool batch_candidate = false;
+
     // ---- per-slice launch units: fuse runs of "large tensor absorbs a small tensor" steps ----------
     {
         bool fuse = !keep && !(d->flags & JB_PLAN_NO_FUSE) && ChainFusionEnabled();
@@ -765,6 +819,13 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         };
         std::vector<char> taken(p->steps.size(), 0);
         const int max_tile = ChainMaxTileBits(p->dtype);
+        // slice batching needs per-slice step matrices: chains whose small operands depend on the slice then
+        // cannot use the (one set per launch) constant-bank register stages
+        int64_t max_slice_elems = 1;
+        for (const Node &n : p->nodes)
+            if (n.slice_dep)
+                max_slice_elems = std::max(max_slice_elems, n.elems);
+        batch_candidate = want_batch != 1 && !keep && p->num_slices > 1 && max_slice_elems <= kBatchMaxElems;
         auto build = [&](const std::vector<int> &order, bool shared_steps) {
         want_shared = shared_steps;
         std::vector<Op> ops;
@@ -785,6 +846,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             chain.kernel = 2;
             chain.x0 = x0;
             std::vector<ChainOperand> operands;
+            bool r_dep = false; // a small operand of the chain depends on the slice
             int x = x0, cur = s;
             while (cur >= 0 && !taken[cur] && static_cast<int>(operands.size()) < kChainMaxSteps) {
                 ChainOperand o;
@@ -792,12 +854,14 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
                 if (!as_operand(cur, x, &o, &r_node))
                     break;
                 operands.push_back(o);
+                const bool dep_now = r_dep || p->nodes[r_node].slice_dep;
                 ChainOp trial;
                 if (MakeChainOp(p->dtype, p->nodes[x0].modes, p->nodes[x0].extent, operands, max_tile,
-                                &trial, nullptr) != 0) {
+                                &trial, nullptr, !(batch_candidate && dep_now)) != 0) {
                     operands.pop_back();
                     break;
                 }
+                r_dep = dep_now;
                 chain.chain = trial;
                 chain.steps.push_back(cur);
                 chain.r_nodes.push_back(r_node);
@@ -872,7 +936,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     if (p->store_cap > 0)
         p->store_off = alloc.Alloc(p->eb * p->result_elems * p->store_cap);
     p->state_off = alloc.Alloc(sizeof(DeviceState));
-    p->list_cap = std::max<int64_t>(std::min<int64_t>(p->num_slices, kMaxListed), 1);
+    p->list_cap = kMaxListed; // ids may repeat: the list length does not depend on the number of slices
     p->list_off = alloc.Alloc(sizeof(long long) * p->list_cap);
     p->descs_off = alloc.Alloc(sizeof(SliceLeafDesc) * std::max<size_t>(p->slice_descs.size(), 1));
     for (size_t e = 0; e < exec.size(); e++) {
@@ -882,7 +946,8 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             p->slice_descs[C.desc].src_off = static_cast<long long>(C.raw_offset / p->eb);
         }
         else {
-            C.offset = alloc.Alloc(C.elems * p->eb);
+            C.per_slice = C.slice_dep;
+            C.offset = (C.per_slice ? salloc : alloc).Alloc(C.elems * p->eb);
         }
         if (keep)
             continue;
@@ -895,10 +960,24 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
             const bool producer_shared = !I.slice_dep;
             if (producer_shared && I.used_by_slice_step)
                 continue;
-            alloc.Free(I.offset, I.elems * p->eb);
+            (I.per_slice ? salloc : alloc).Free(I.offset, I.elems * p->eb);
         }
     }
-    p->arena_bytes = alloc.Peak();
+    p->slice_base = OffsetAllocator::Align(alloc.Peak());
+    p->slice_bytes = OffsetAllocator::Align(salloc.Peak());
+    p->batch = 1;
+    if (batch_candidate) {
+        // as many slices per launch as keep the replicated region small (L2-sized working sets are the point)
+        int64_t b = want_batch > 1 ? want_batch : 64;
+        b = std::min<int64_t>(b, p->num_slices);
+        b = std::min<int64_t>(b, std::max<int64_t>(1, static_cast<int64_t>((size_t(1) << 30) / p->slice_bytes)));
+        b = std::min<int64_t>(b, 1024);
+        int pow2 = 1;
+        while (2 * pow2 <= b)
+            pow2 *= 2;
+        p->batch = pow2;
+    }
+    p->arena_bytes = p->slice_base + static_cast<size_t>(p->batch) * p->slice_bytes;
 
     // ---- statistics -----------------------------------------------------------------------------------
     jb_plan_stats_t &S = p->stats;
@@ -954,6 +1033,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         }
     }
     S.arena_bytes = p->arena_bytes;
+    S.batch = p->batch;
 
     if (!dry) {
         JB_TRY(AllocDeviceResources(p));
@@ -991,6 +1071,9 @@ int jb_plan_clone(const jb_plan *src, int device, jb_plan **out)
     p->num_slices = src->num_slices;
     p->slice_descs = src->slice_descs;
     p->arena_bytes = src->arena_bytes;
+    p->batch = src->batch;
+    p->slice_base = src->slice_base;
+    p->slice_bytes = src->slice_bytes;
     p->ws_off = src->ws_off;
     p->ws_bytes = src->ws_bytes;
     p->acc_off = src->acc_off;
@@ -1029,6 +1112,10 @@ int jb_plan_destroy(jb_plan *p)
         cudaGraphExecDestroy(p->graph_exec);
     if (p->graph)
         cudaGraphDestroy(p->graph);
+    if (p->graph_exec1)
+        cudaGraphExecDestroy(p->graph_exec1);
+    if (p->graph1)
+        cudaGraphDestroy(p->graph1);
     if (p->shared_exec)
         cudaGraphExecDestroy(p->shared_exec);
     if (p->shared_graph)
@@ -1189,8 +1276,7 @@ int jb_plan_node(jb_plan *p, int32_t node, void *h_out, int64_t *elems)
         *elems = n.elems;
     if (h_out) {
         JB_CUDA(cudaSetDevice(p->device));
-        JB_CUDA(cudaMemcpyAsync(h_out, p->arena + n.offset, p->eb * n.elems, cudaMemcpyDeviceToHost,
-                                p->stream));
+        JB_CUDA(cudaMemcpyAsync(h_out, NodePtr(p, node), p->eb * n.elems, cudaMemcpyDeviceToHost, p->stream));
         JB_CUDA(cudaStreamSynchronize(p->stream));
     }
     return 0;
@@ -1315,10 +1401,10 @@ int jb_plan_profile_ops(jb_plan *p, int64_t slice, int reps, float *ms, int32_t 
     std::vector<double> total(p->ops.size(), 0.0);
     for (int r = 0; r < reps + 1; r++) {
         SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), slice, -1, 0);
-        JB_TRY(LaunchSliceViews(p));
+        JB_TRY(LaunchSliceViews(p, 1));
         for (size_t i = 0; i < p->ops.size(); i++) {
             JB_CUDA(cudaEventRecord(ev[i], p->stream));
-            JB_TRY(LaunchOp(p, p->ops[i]));
+            JB_TRY(LaunchOp(p, p->ops[i], 1));
         }
         JB_CUDA(cudaEventRecord(ev.back(), p->stream));
         JB_CUDA(cudaStreamSynchronize(p->stream));

@@ -86,7 +86,7 @@ class ContractionPlan:
 
     def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), device: int = 0, keep_intermediates=False,
                  use_graph=True, store_results=False, path: Optional[Sequence[Sequence[int]]] = None,
-                 fuse=True, dry_run=False):
+                 fuse=True, dry_run=False, batch=0):
         self.net = net
         self.sliced = list(sliced)
         self.device = device
@@ -117,7 +117,7 @@ class ContractionPlan:
             JB_PLAN_STORE_RESULTS if store_results else 0) | (0 if fuse else JB_PLAN_NO_FUSE) | (
             JB_PLAN_DRY_RUN if dry_run else 0)
         desc = NetworkDesc(dtype_code(self.dtype), device, n, self._rank, self._extent, self._mode, self._data,
-                           len(steps), self._path, len(self.sliced), self._sliced, flags)
+                           len(steps), self._path, len(self.sliced), self._sliced, flags, batch)
         self._h = C.c_void_p()
         check(lib().jb_plan_create(C.byref(desc), C.byref(self._h)))
         st = PlanStats()
@@ -282,7 +282,7 @@ class MultiPlan:
 
     def __init__(self, net: NetworkFile, sliced: Sequence[str] = (), lanes: int = 2, device: int = 0,
                  devices: Optional[Sequence[int]] = None, keep_intermediates=False, use_graph=True,
-                 store_results=False, path: Optional[Sequence[Sequence[int]]] = None, fuse=True):
+                 store_results=False, path: Optional[Sequence[Sequence[int]]] = None, fuse=True, batch=0):
         if not 0 <= lanes <= self.MAX_LANES:
             raise ValueError(f"lanes must be in 0..{self.MAX_LANES} (0 = automatic)")
         self.net = net
@@ -313,7 +313,7 @@ class MultiPlan:
         flags = (JB_PLAN_KEEP_INTERMEDIATES if keep_intermediates else 0) | (0 if use_graph else JB_PLAN_NO_GRAPH) | (
             JB_PLAN_STORE_RESULTS if store_results else 0) | (0 if fuse else JB_PLAN_NO_FUSE)
         desc = NetworkDesc(dtype_code(self.dtype), self.devices[0], n, self._rank, self._extent, self._mode, self._data,
-                           len(steps), self._path, len(self.sliced), self._sliced, flags)
+                           len(steps), self._path, len(self.sliced), self._sliced, flags, batch)
         devs = (C.c_int * len(self.devices))(*self.devices)
         self._h = C.c_void_p()
         check(lib().jb_multi_create(C.byref(desc), len(self.devices), devs, lanes, C.byref(self._h)))

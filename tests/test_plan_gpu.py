@@ -232,3 +232,47 @@ def test_gbs_fock8_c128_matches_reference_golden(data_dir):
         assert plan.num_slices == 64
         got = complex(plan.amplitude().reshape(-1)[0])
     assert abs(got - want) / abs(want) < 1e-12, (got, want)
+
+
+def test_slice_batching_is_bit_identical(data_dir):
+    """Slice batching (several slices per launch: per-slice tensors replicated `batch` times in the arena, kernels
+    take the slice from blockIdx.y/z) must not change a single bit: same arithmetic per slice, same accumulation
+    order.  m10 / s=10 (batch 64 by default), uneven counts (whole batches + remainder), explicit id lists, per-slice
+    results, and a random network with non-power-of-two extents (TTGT units are looped, not batched)."""
+    from jet_b200 import ContractionPlan, NetworkFile
+    net = NetworkFile.load(os.path.join(data_dir, "m10.json"), np.complex64)
+    sliced = "p7 s7 h4 m1 m2 I2 V4 z2 t4 C1".split()
+    with ContractionPlan(net, sliced, batch=1, store_results=True) as one, \
+            ContractionPlan(net, sliced, store_results=True) as auto, \
+            ContractionPlan(net, sliced, batch=8, store_results=True) as eight:
+        assert one.stats.batch == 1 and auto.stats.batch == 64 and eight.stats.batch == 8
+        for first, count in ((0, 200), (37, 75), (1000, 24), (5, 3)):
+            want = None
+            for plan in (one, auto, eight):
+                plan.reset()
+                plan.run(first, count)
+                got = plan.result().reshape(-1)[0]
+                per = [complex(plan.slice_result(k).reshape(-1)[0]) for k in (0, count // 2, count - 1)]
+                if want is None:
+                    want = (got, per)
+                else:
+                    assert got == want[0] and per == want[1], (first, count, plan.stats.batch)
+        ids = [3, 1000, 17, 17, 512, 9, 77, 640, 2, 1023, 0]
+        ref = one.amplitude(ids).reshape(-1)[0]
+        assert auto.amplitude(ids).reshape(-1)[0] == ref and eight.amplitude(ids).reshape(-1)[0] == ref
+    rng = np.random.default_rng(11)
+
+    def rc(shape):
+        n = int(np.prod(shape))
+        return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex128).reshape(shape)
+
+    tensors = [(["a", "b", "s"], rc([3, 4, 2])), (["b", "c", "t"], rc([4, 2, 4])), (["c", "d", "s"], rc([2, 5, 2])),
+               (["d", "a", "t", "u"], rc([5, 3, 4, 2])), (["u", "o"], rc([2, 3]))]
+    path = [(0, 1), (2, 3), (5, 6), (7, 4)]
+    with ContractionPlan(NetworkFile(tensors, path), ["s", "t"], batch=1) as one, \
+            ContractionPlan(NetworkFile(tensors, path), ["s", "t"], batch=4) as four:
+        assert four.stats.batch == 4
+        a, b = one.amplitude(), four.amplitude()
+        assert np.array_equal(a, b)
+        want = np.asarray(jo.amplitude(jo.Network(tensors, path), ["s", "t"]))
+        assert np.linalg.norm(b.reshape(-1) - want.reshape(-1)) / np.linalg.norm(want) < 1e-12

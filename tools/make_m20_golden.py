@@ -8,7 +8,7 @@ indices to slice for a small peak (the value of a slice does not depend on the c
 sub-slices go through the reference's own sliced flow (jet_sliced.cpp: SliceIndices copies -> AddContractionTasks
 -> AddReductionTask -> Contract); the reduction result IS the slice amplitude — an identity of the contraction,
 not an approximation.  Run in the container that has /root/reference:
-    python tools/make_m20_golden.py [--stem sycamore53_m20] [--peak-log2 24] [slice ids ...]
+    python tools/make_m20_golden.py [--stem sycamore53_m20] [--peak-log2 24] [--dtypes complex128] [slice ids ...]
 The complex128 value is the truth the tests compare against (1e-12 for the complex128 engine; the complex64 engine
 is compared with it at the accuracy the conditioning of the sum allows, see tests/test_m20_synth.py)."""
 import json
@@ -22,12 +22,14 @@ from oracle import ref  # noqa: E402
 
 DATA = os.path.join(ROOT, "data")
 argv = sys.argv[1:]
-stem, peak_log2 = "sycamore53_m20", 24
+stem, peak_log2, only = "sycamore53_m20", 24, []
 while argv and argv[0].startswith("--"):
     if argv[0] == "--stem":
         stem, argv = argv[1], argv[2:]
     elif argv[0] == "--peak-log2":
         peak_log2, argv = int(argv[1]), argv[2:]
+    elif argv[0] == "--dtypes":
+        only, argv = argv[1].split(","), argv[2:]
     else:
         raise SystemExit("unknown option " + argv[0])
 ids = [int(a) for a in argv] or [0, 1234567]
@@ -54,15 +56,31 @@ print(f"{stem}: {len(sliced)} sliced indices + {len(extra)} extra {extra} -> {n_
 out_path = os.path.join(DATA, stem + ".golden.json")
 gold = json.load(open(out_path)) if os.path.exists(out_path) else {}
 ref.set_blas_threads(1)
-threads = os.cpu_count() or 1
-for v in ids:
-    e = gold.setdefault(str(v), {})
-    e["extra_indices"], e["sub_slices"] = extra, n_sub
-    for dt, key in (("complex64", ""), ("complex128", "_c128")):
-        if ("re" + key) in e:
-            continue
-        r, sec, fl = ref.network(text, dt, full, v * n_sub, mode=2, threads=threads, num_slices=n_sub)
-        e["re" + key], e["im" + key] = float(r[0].real), float(r[0].imag)
-        e["jet_flops_reference"], e["ref_seconds_here" + key] = fl, sec
-        print(v, dt, r[0], f"{sec:.1f} s", flush=True)
-        json.dump(gold, open(out_path, "w"), indent=1)
+
+
+def _one(args):
+    """One sub-slice through the reference's TaskBasedContractor (+ deletion tasks: bounded memory), 2 threads."""
+    dt, sub_id = args
+    r, sec, fl = ref.network(text, dt, full, sub_id, mode=2, threads=2, num_slices=1)
+    return complex(r[0]), sec, fl
+
+
+if __name__ == "__main__":
+    import multiprocessing as mp
+    import time
+
+    workers = max(1, min(4, (os.cpu_count() or 2) // 2))
+    for v in ids:
+        e = gold.setdefault(str(v), {})
+        e["extra_indices"], e["sub_slices"] = extra, n_sub
+        for dt, key in (("complex64", ""), ("complex128", "_c128")):
+            if ("re" + key) in e or (only and dt not in only):
+                continue
+            t0 = time.time()
+            with mp.Pool(workers) as pool:
+                parts = pool.map(_one, [(dt, v * n_sub + j) for j in range(n_sub)], chunksize=1)
+            total = sum(p[0] for p in parts)  # summed in complex128 (Python complex), sub-slice order
+            e["re" + key], e["im" + key] = float(total.real), float(total.imag)
+            e["jet_flops_reference"], e["ref_seconds_here" + key] = sum(p[2] for p in parts), time.time() - t0
+            print(v, dt, total, f"{time.time() - t0:.1f} s", flush=True)
+            json.dump(gold, open(out_path, "w"), indent=1)
