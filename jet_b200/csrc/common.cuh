@@ -114,6 +114,10 @@ struct ContractPlan {
     // ttgt, complex128: the DMMA GEMM reads A in its original layout (no permuted copy of A)
     bool gather_a = false;
     std::vector<int> a_free_bits, a_common_bits; // address bits of A's free / contracted index bits, ascending
+    // ttgt, DOTU / GEMV corner with power-of-two extents: both operands are read ONCE in their original layouts
+    // (no permuted copies): blob = DotGatherParams (contract.cu)
+    bool gather_dot = false;
+    std::vector<unsigned char> dot_blob;
     // stream kernel parameters (opaque blob, see contract.cu)
     std::vector<unsigned char> stream_blob;
     int launches = 1;

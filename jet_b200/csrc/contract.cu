@@ -198,6 +198,179 @@ __global__ void __launch_bounds__(kStreamThreads, (KC * XT * sizeof(R) <= 32 && 
     }
 }
 
+
+// ---- packed variant for FMA-heavy shapes (complex64, K >= 4, 4 <= Y <= 32) --------------------------------------
+// The kernel above issues four scalar FMAs per complex multiply-add and re-reads the streamed operand once per
+// group of NR outputs when K does not fit its register chunk; at K = N = 16 it is issue-bound at 25 TFLOP/s (37 % of
+// the FMA pipe).  Here every output of a row lives in a packed accumulator (fma.rn.f32x2: two IEEE FMAs per
+// instruction, the same two FMAs per component in the same order as the scalar code), the resident operand sits in
+// shared memory as (b.x, b.y, -b.y, b.x) so that one 16-byte broadcast load feeds both packed FMAs of XT rows, and
+// the streamed operand is read exactly once, KC values of k at a time.
+__device__ __forceinline__ unsigned long long SPack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 SUnpack2(unsigned long long v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+template <int KC, int Y, int XT>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+    StreamPackedKernel(const float2 *__restrict__ S, const float2 *__restrict__ Rsd, float2 *__restrict__ out,
+                       const __grid_constant__ StreamParams p, const long long stride_s, const long long stride_r,
+                       const long long stride_o)
+{
+    S = reinterpret_cast<const float2 *>(reinterpret_cast<const unsigned char *>(S) + blockIdx.y * stride_s);
+    Rsd = reinterpret_cast<const float2 *>(reinterpret_cast<const unsigned char *>(Rsd) + blockIdx.y * stride_r);
+    out = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(out) + blockIdx.y * stride_o);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *Rm = reinterpret_cast<float4 *>(smem_raw); // [K][Y] as (b.x, b.y, -b.y, b.x)
+    const int tid = threadIdx.x;
+    const int K = 1 << p.log_k;
+    for (int e = tid; e < K * Y; e += kStreamThreads) {
+        const unsigned k = e / Y, y = e % Y;
+        const float2 b = __ldg(Rsd + (ScatterBits(k, p.rk, p.log_k) | ScatterBits(y, p.ry, p.log_y)));
+        Rm[e] = make_float4(b.x, b.y, -b.y, b.x);
+    }
+    constexpr int kLogKC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
+    unsigned long long koff_lo[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) {
+        unsigned long long r = 0;
+#pragma unroll
+        for (int q = 0; (1 << q) < KC; q++)
+            if (kk & (1 << q))
+                r |= 1ull << p.cs[q];
+        koff_lo[kk] = r;
+    }
+    const int n_kchunks = K / KC;
+    __syncthreads();
+
+    const long long tile = static_cast<long long>(kStreamThreads) * XT;
+    for (long long x0 = static_cast<long long>(blockIdx.x) * tile; x0 < p.x_count;
+         x0 += static_cast<long long>(gridDim.x) * tile) {
+        long long x[XT];
+        unsigned long long sbase[XT];
+        bool ok[XT];
+#pragma unroll
+        for (int j = 0; j < XT; j++) {
+            x[j] = x0 + j * kStreamThreads + tid;
+            ok[j] = x[j] < p.x_count;
+            sbase[j] = InsertZeros(static_cast<unsigned long long>(ok[j] ? x[j] : 0), p.cs, p.log_k);
+        }
+        unsigned long long acc[XT][Y];
+#pragma unroll
+        for (int j = 0; j < XT; j++)
+#pragma unroll
+            for (int yy = 0; yy < Y; yy++)
+                acc[j][yy] = 0ull;
+        for (int kc = 0; kc < n_kchunks; kc++) {
+            const unsigned long long khi =
+                ScatterBits(static_cast<unsigned long long>(kc), p.cs + kLogKC, p.log_k - kLogKC);
+            float2 a[XT][KC];
+#pragma unroll
+            for (int j = 0; j < XT; j++)
+#pragma unroll
+                for (int kk = 0; kk < KC; kk++)
+                    a[j][kk] = ok[j] ? __ldg(S + (sbase[j] | khi | koff_lo[kk])) : float2{0.f, 0.f};
+            const float4 *rrow = Rm + (kc * KC) * Y;
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                unsigned long long ax[XT], ay[XT];
+#pragma unroll
+                for (int j = 0; j < XT; j++) {
+                    ax[j] = SPack2(a[j][kk].x, a[j][kk].x);
+                    ay[j] = SPack2(a[j][kk].y, a[j][kk].y);
+                }
+#pragma unroll
+                for (int yy = 0; yy < Y; yy++) {
+                    const float4 b = rrow[kk * Y + yy];
+                    const unsigned long long b0 = SPack2(b.x, b.y), b1 = SPack2(b.z, b.w);
+#pragma unroll
+                    for (int j = 0; j < XT; j++) {
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][yy]) : "l"(ax[j]), "l"(b0));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][yy]) : "l"(ay[j]), "l"(b1));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < XT; j++) {
+            if (!ok[j])
+                continue;
+            if (p.out_y_shift == 0) {
+                float2 *dst = out + (static_cast<unsigned long long>(x[j]) << p.out_x_shift);
+#pragma unroll
+                for (int yy = 0; yy < Y; yy += 2) {
+                    const float2 v0 = SUnpack2(acc[j][yy]), v1 = SUnpack2(acc[j][yy + 1]);
+                    *reinterpret_cast<float4 *>(dst + yy) = make_float4(v0.x, v0.y, v1.x, v1.y);
+                }
+            }
+            else {
+#pragma unroll
+                for (int yy = 0; yy < Y; yy++)
+                    out[(static_cast<unsigned long long>(yy) << p.out_y_shift) + static_cast<unsigned long long>(x[j])] =
+                        SUnpack2(acc[j][yy]);
+            }
+        }
+    }
+}
+
+template <int KC, int Y, int XT>
+int LaunchStreamPackedT(const StreamParams &p, const void *s, const void *r, void *out, cudaStream_t stream, int batch,
+                        long long ss, long long sr, long long so)
+{
+    const long long tile = static_cast<long long>(kStreamThreads) * XT;
+    const long long tiles = (p.x_count + tile - 1) / tile;
+    const size_t smem = sizeof(float4) << (p.log_k + p.log_y);
+    auto kernel = StreamPackedKernel<KC, Y, XT>;
+    if (smem > 48 * 1024)
+        JB_TRY(EnsureDynamicSmem(reinterpret_cast<const void *>(kernel), smem));
+    const long long resident = static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kStreamThreads, smem);
+    const int grid = static_cast<int>(std::min<long long>(tiles, std::max<long long>(1, resident / batch)));
+    kernel<<<dim3(grid, batch), kStreamThreads, smem, stream>>>(static_cast<const float2 *>(s), static_cast<const float2 *>(r),
+                                                                static_cast<float2 *>(out), p, ss, sr, so);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool StreamPackedEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_STREAM_NO_PACKED");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
+}
+
+// returns -1 when the shape is not served by the packed kernel
+int LaunchStreamPacked(const StreamParams &p, const void *s, const void *r, void *out, cudaStream_t stream, int batch,
+                       long long ss, long long sr, long long so)
+{
+    const int k = 1 << p.log_k, y = 1 << p.log_y;
+    if (!StreamPackedEnabled() || k < 4 || y < 4 || y > 32 || k * y < 32)
+        return -1;
+    if (k == 4) {
+        if (y == 8)
+            return LaunchStreamPackedT<4, 8, 2>(p, s, r, out, stream, batch, ss, sr, so);
+        if (y == 16)
+            return LaunchStreamPackedT<4, 16, 2>(p, s, r, out, stream, batch, ss, sr, so);
+        return y == 32 ? LaunchStreamPackedT<4, 32, 1>(p, s, r, out, stream, batch, ss, sr, so) : -1;
+    }
+    if (y == 4)
+        return LaunchStreamPackedT<8, 4, 2>(p, s, r, out, stream, batch, ss, sr, so);
+    if (y == 8)
+        return LaunchStreamPackedT<8, 8, 2>(p, s, r, out, stream, batch, ss, sr, so);
+    if (y == 16)
+        return LaunchStreamPackedT<8, 16, 2>(p, s, r, out, stream, batch, ss, sr, so);
+    return LaunchStreamPackedT<8, 32, 1>(p, s, r, out, stream, batch, ss, sr, so);
+}
+
 template <typename R, int KC, int NR>
 int LaunchStreamT(const StreamParams &p, const void *s, const void *r, void *out,
                   cudaStream_t stream, int batch, long long stride_s, long long stride_r, long long stride_o)
@@ -241,6 +414,11 @@ int LaunchStream(const StreamParams &p, const void *s, const void *r, void *out,
                  cudaStream_t stream, int batch = 1, long long ss = 0, long long sr = 0, long long so = 0)
 {
     JB_REQUIRE(batch >= 1 && batch <= 65535, "contract: batch out of range");
+    if constexpr (sizeof(R) == 4) {
+        const int rc = LaunchStreamPacked(p, s, r, out, stream, batch, ss, sr, so);
+        if (rc >= 0)
+            return rc;
+    }
     const int k = 1 << p.log_k;
     if (k >= 8)
         return LaunchStreamK<R, 8>(p, s, r, out, stream, batch, ss, sr, so);
@@ -421,6 +599,150 @@ __global__ void __launch_bounds__(32)
         }
         out[threadIdx.x] = C{static_cast<R>(x), static_cast<R>(y)};
     }
+}
+
+
+// ---- the same corner with both operands in their ORIGINAL tensor layouts -------------------------------------------
+// The last step of a closed network contracts two large tensors over (almost) all their indices (m=20: two rank-31
+// tensors, K = 2^29, M = N = 4).  Through TTGT that is two full permutations before the dot: three passes over
+// memory instead of one.  Here nothing is permuted: the contracted index bits are split into TILE bits — the lowest
+// contracted address bits of A and the lowest ones of B — and OUTER bits.  A CTA walks one tile at a time in A's
+// address order (coalesced); the matching B elements of the tile are a bit-permutation of the same tile, spread
+// over a few KB that the walk touches completely, so B's sectors are fetched from DRAM once and served from L1
+// until the tile is done.  Partial sums in double, combined in a fixed order (deterministic), as above.
+constexpr int kDotMaxTileBits = 11;
+constexpr int kDotMaxOuterBits = 56;
+struct DotGatherParams {
+    int log_tile, log_outer, log_m, log_n;
+    uint8_t tile_a[kDotMaxTileBits], tile_b[kDotMaxTileBits];   // address bit in A / B of tile bit q (A-ascending)
+    uint8_t outer_a[kDotMaxOuterBits], outer_b[kDotMaxOuterBits]; // ... of outer bit q
+    uint8_t m_a[2], n_b[2];                                       // address bit in A of m bit q / in B of n bit q
+};
+
+template <typename R, int M, int N>
+__global__ void __launch_bounds__(256)
+    DotGatherKernel(const typename Cx<R>::type *__restrict__ A, const typename Cx<R>::type *__restrict__ B,
+                    double2 *__restrict__ partial, const __grid_constant__ DotGatherParams p)
+{
+    using C = typename Cx<R>::type;
+    double2 acc[M][N];
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+        for (int n = 0; n < N; n++)
+            acc[m][n] = double2{0.0, 0.0};
+    unsigned long long am[M], bn[N];
+#pragma unroll
+    for (int m = 0; m < M; m++)
+        am[m] = ScatterBits(static_cast<unsigned long long>(m), p.m_a, p.log_m);
+#pragma unroll
+    for (int n = 0; n < N; n++)
+        bn[n] = ScatterBits(static_cast<unsigned long long>(n), p.n_b, p.log_n);
+    // tile index = thread (low 8 bits) | pass (the rest): both address contributions are additive
+    const int tb = p.log_tile < 8 ? p.log_tile : 8;
+    const unsigned long long ta = ScatterBits(threadIdx.x, p.tile_a, tb), tbb = ScatterBits(threadIdx.x, p.tile_b, tb);
+    const int passes = p.log_tile > 8 ? 1 << (p.log_tile - 8) : 1;
+    const bool active = static_cast<int>(threadIdx.x) < (1 << tb);
+    const long long tiles = 1ll << p.log_outer;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const unsigned long long oa = ScatterBits(static_cast<unsigned long long>(t), p.outer_a, p.log_outer);
+        const unsigned long long ob = ScatterBits(static_cast<unsigned long long>(t), p.outer_b, p.log_outer);
+        for (int ps = 0; ps < passes; ps++) {
+            const unsigned long long pa = oa | ta | ScatterBits(static_cast<unsigned long long>(ps), p.tile_a + 8, p.log_tile - tb);
+            const unsigned long long pb = ob | tbb | ScatterBits(static_cast<unsigned long long>(ps), p.tile_b + 8, p.log_tile - tb);
+            if (!active)
+                continue;
+            C a[M], b[N];
+#pragma unroll
+            for (int m = 0; m < M; m++)
+                a[m] = __ldg(A + (pa | am[m]));
+#pragma unroll
+            for (int n = 0; n < N; n++)
+                b[n] = __ldg(B + (pb | bn[n]));
+#pragma unroll
+            for (int m = 0; m < M; m++)
+#pragma unroll
+                for (int n = 0; n < N; n++) {
+                    const double ar = a[m].x, ai = a[m].y, br = b[n].x, bi = b[n].y;
+                    acc[m][n].x += ar * br - ai * bi;
+                    acc[m][n].y += ar * bi + ai * br;
+                }
+        }
+    }
+    __shared__ double2 red[8][M * N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            double x = acc[m][n].x, y = acc[m][n].y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                x += __shfl_down_sync(0xffffffffu, x, o);
+                y += __shfl_down_sync(0xffffffffu, y, o);
+            }
+            if (lane == 0)
+                red[warp][m * N + n] = double2{x, y};
+        }
+    __syncthreads();
+    if (threadIdx.x < M * N) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < 8; w++) {
+            x += red[w][threadIdx.x].x;
+            y += red[w][threadIdx.x].y;
+        }
+        partial[static_cast<long long>(blockIdx.x) * (M * N) + threadIdx.x] = double2{x, y};
+    }
+}
+
+int DotGatherBlocks(const DotGatherParams &p)
+{
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(1ll << p.log_outer, NumSMs() * 8ll)));
+}
+
+template <typename R, int M>
+int LaunchDotGatherN(const DotGatherParams &p, const void *a, const void *b, void *ws, int blocks, cudaStream_t stream)
+{
+    using C = typename Cx<R>::type;
+    const C *A = static_cast<const C *>(a);
+    const C *B = static_cast<const C *>(b);
+    double2 *P = static_cast<double2 *>(ws);
+    if (p.log_n == 0)
+        DotGatherKernel<R, M, 1><<<blocks, 256, 0, stream>>>(A, B, P, p);
+    else if (p.log_n == 1)
+        DotGatherKernel<R, M, 2><<<blocks, 256, 0, stream>>>(A, B, P, p);
+    else
+        DotGatherKernel<R, M, 4><<<blocks, 256, 0, stream>>>(A, B, P, p);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+int LaunchDotGather(const DotGatherParams &p, const void *a, const void *b, void *c, void *ws, size_t ws_bytes,
+                    cudaStream_t stream)
+{
+    const int blocks = DotGatherBlocks(p);
+    const int mn = 1 << (p.log_m + p.log_n);
+    JB_REQUIRE(ws != nullptr && ws_bytes >= sizeof(double2) * static_cast<size_t>(blocks) * mn, "gemm: workspace too small");
+    if (p.log_m == 0)
+        JB_TRY((LaunchDotGatherN<R, 1>(p, a, b, ws, blocks, stream)));
+    else if (p.log_m == 1)
+        JB_TRY((LaunchDotGatherN<R, 2>(p, a, b, ws, blocks, stream)));
+    else
+        JB_TRY((LaunchDotGatherN<R, 4>(p, a, b, ws, blocks, stream)));
+    SmallMnFinishKernel<R><<<1, 32, 0, stream>>>(static_cast<const double2 *>(ws),
+                                                static_cast<typename Cx<R>::type *>(c), mn, blocks);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool DotGatherEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_DISABLE_DOT_GATHER");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
 }
 
 bool SmallMnEligible(int64_t m, int64_t n, int64_t k)
@@ -859,6 +1181,81 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
     P.kernel = 1;
     P.perm_a.clear();
     P.perm_b.clear();
+    // DOTU / GEMV corner with a long K: read both operands once, where they lie (DotGatherKernel)
+    if (pow2 && DotGatherEnabled() && SmallMnEligible(P.m, P.n, P.k) && P.k >= (1 << 16)) {
+        std::vector<int> lo_a(rank_a), lo_b(rank_b);
+        int na = 0, nb = 0;
+        for (int i = rank_a - 1; i >= 0; i--) {
+            lo_a[i] = na;
+            na += Log2(extent_a[i]);
+        }
+        for (int j = rank_b - 1; j >= 0; j--) {
+            lo_b[j] = nb;
+            nb += Log2(extent_b[j]);
+        }
+        struct KBit {
+            int a, b;
+        };
+        std::vector<KBit> kb;
+        for (size_t q = 0; q < common_a.size(); q++)
+            for (int bbit = 0; bbit < Log2(extent_a[common_a[q]]); bbit++)
+                kb.push_back({lo_a[common_a[q]] + bbit, lo_b[common_b[q]] + bbit});
+        DotGatherParams dp;
+        std::memset(&dp, 0, sizeof(dp));
+        // free index bits, least significant first (row-major over the free axes, last axis fastest)
+        for (auto it = left.rbegin(); it != left.rend(); ++it)
+            for (int bbit = 0; bbit < Log2(extent_a[*it]); bbit++)
+                dp.m_a[dp.log_m++] = static_cast<uint8_t>(lo_a[*it] + bbit);
+        for (auto it = right.rbegin(); it != right.rend(); ++it)
+            for (int bbit = 0; bbit < Log2(extent_b[*it]); bbit++)
+                dp.n_b[dp.log_n++] = static_cast<uint8_t>(lo_b[*it] + bbit);
+        // tile bits: the 6 lowest contracted address bits of A and the 5 lowest of B (a bit may be both)
+        std::vector<KBit> by_a = kb, by_b = kb;
+        std::sort(by_a.begin(), by_a.end(), [](const KBit &x, const KBit &y) { return x.a < y.a; });
+        std::sort(by_b.begin(), by_b.end(), [](const KBit &x, const KBit &y) { return x.b < y.b; });
+        std::vector<KBit> tile;
+        auto in_tile = [&](const KBit &v) {
+            for (const KBit &t : tile)
+                if (t.a == v.a)
+                    return true;
+            return false;
+        };
+        for (size_t q = 0; q < by_a.size() && tile.size() < 6; q++)
+            tile.push_back(by_a[q]);
+        for (size_t q = 0; q < by_b.size() && static_cast<int>(tile.size()) < kDotMaxTileBits; q++) {
+            if (q >= 5)
+                break;
+            if (!in_tile(by_b[q]))
+                tile.push_back(by_b[q]);
+        }
+        std::sort(tile.begin(), tile.end(), [](const KBit &x, const KBit &y) { return x.a < y.a; });
+        std::vector<KBit> outer;
+        for (const KBit &v : by_a)
+            if (!in_tile(v))
+                outer.push_back(v);
+        if (static_cast<int>(outer.size()) <= kDotMaxOuterBits && na <= 62 && nb <= 62) {
+            dp.log_tile = static_cast<int>(tile.size());
+            dp.log_outer = static_cast<int>(outer.size());
+            for (size_t q = 0; q < tile.size(); q++) {
+                dp.tile_a[q] = static_cast<uint8_t>(tile[q].a);
+                dp.tile_b[q] = static_cast<uint8_t>(tile[q].b);
+            }
+            for (size_t q = 0; q < outer.size(); q++) {
+                dp.outer_a[q] = static_cast<uint8_t>(outer[q].a);
+                dp.outer_b[q] = static_cast<uint8_t>(outer[q].b);
+            }
+            P.gather_dot = true;
+            P.dot_blob.resize(sizeof(dp));
+            std::memcpy(P.dot_blob.data(), &dp, sizeof(dp));
+            P.permute_a = P.permute_b = false;
+            P.gemm_kind = JB_GEMM_SMALL_MN;
+            P.launches = 2;
+            P.ws_gemm_off = 0;
+            P.ws_gemm_bytes = sizeof(double2) * static_cast<size_t>(DotGatherBlocks(dp)) * static_cast<size_t>(P.m * P.n);
+            P.ws_bytes = (P.ws_gemm_bytes + 255) & ~size_t(255);
+            return 0;
+        }
+    }
     // complex64, short M and a long N: the tensor-core GEMM wastes most of its 128-row tile on M, and its
     // B' expansion quadruples the traffic of the LARGE operand.  Compute C^T = B^T A^T instead: B (as
     // right ++ common) is the GEMM's row operand, A (as common ++ left) the expanded one, and the small
@@ -970,6 +1367,13 @@ int LaunchContract(const ContractPlan &P, const void *a, const void *b, void *c,
         return 0;
     }
     JB_REQUIRE(P.ws_bytes == 0 || ws != nullptr, "contract: workspace required");
+    if (P.gather_dot) {
+        DotGatherParams dp;
+        std::memcpy(&dp, P.dot_blob.data(), sizeof(dp));
+        if (P.dtype == JB_C64)
+            return LaunchDotGather<float>(dp, a, b, c, ws, P.ws_bytes, stream);
+        return LaunchDotGather<double>(dp, a, b, c, ws, P.ws_bytes, stream);
+    }
     unsigned char *w = static_cast<unsigned char *>(ws);
     const void *at = a, *bt = b;
     if (P.permute_a) {

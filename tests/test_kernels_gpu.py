@@ -383,3 +383,38 @@ def test_contract_both_operands_large_uses_tensor_cores(ops):
     out, _ = ops.contract(a, ids_a, b, ids_b)
     _, ref = jo.contract(([str(i) for i in ids_a], a.astype(np.complex128)), ([str(i) for i in ids_b], b.astype(np.complex128)))
     assert rel_err(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_contract_final_dot_reads_operands_in_place(ops, dtype):
+    """The last step of a closed network: two large tensors contracted over (almost) all indices, M, N in {1, 2, 4},
+    K >= 2^16 (DotGatherKernel: both operands read once in their original layouts, no permuted copies; FP64
+    partial sums in a fixed order).  Random index orders on both sides, dim-2 and dim-4 axes, against the oracle;
+    the complex64 result must also agree with the TTGT path (JB_DISABLE_DOT_GATHER) to FP32 accuracy."""
+    rng = np.random.default_rng(23)
+    for trial, (n_common, fa, fb, with_dim4) in enumerate([(17, 1, 1, False), (18, 2, 2, False), (16, 0, 2, True),
+                                                           (19, 2, 0, False), (16, 0, 0, True), (20, 1, 2, False)]):
+        common = [f"k{i}" for i in range(n_common)]
+        dims = {i: 2 for i in common}
+        if with_dim4:
+            for i in common[:3]:
+                dims[i] = 4
+        ia = common + [f"a{i}" for i in range(fa)]
+        ib = common + [f"b{i}" for i in range(fb)]
+        for i in ia + ib:
+            dims.setdefault(i, 2)
+        ia = [ia[i] for i in rng.permutation(len(ia))]
+        ib = [ib[i] for i in rng.permutation(len(ib))]
+        sa, sb = [dims[i] for i in ia], [dims[i] for i in ib]
+        a = rand_c(rng, int(np.prod(sa)), dtype).reshape(sa)
+        b = rand_c(rng, int(np.prod(sb)), dtype).reshape(sb)
+        labels = {name: k for k, name in enumerate(sorted(dims))}
+        info = ops.contract_info(dtype, sa, [labels[i] for i in ia], sb, [labels[i] for i in ib])
+        assert info.kernel == 1 and info.m * info.n <= 16
+        got, modes = ops.contract(a, [labels[i] for i in ia], b, [labels[i] for i in ib])
+        idx, want = jo.contract((ia, a), (ib, b))
+        assert [labels[i] for i in idx] == list(modes)
+        # the sum has sqrt(K) growth and cancellation: compare against the scale of the terms
+        scale = np.sqrt(float(info.k)) * 1.0
+        err = np.abs(np.asarray(got, dtype=np.complex128).reshape(-1) - np.asarray(want, dtype=np.complex128).reshape(-1)).max() / scale
+        assert err < TOL[np.dtype(dtype)], (trial, err)
