@@ -199,178 +199,6 @@ __global__ void __launch_bounds__(kStreamThreads, (KC * XT * sizeof(R) <= 32 && 
 }
 
 
-// ---- packed variant for FMA-heavy shapes (complex64, K >= 4, 4 <= Y <= 32) --------------------------------------
-// The kernel above issues four scalar FMAs per complex multiply-add and re-reads the streamed operand once per
-// group of NR outputs when K does not fit its register chunk; at K = N = 16 it is issue-bound at 25 TFLOP/s (37 % of
-// the FMA pipe).  Here every output of a row lives in a packed accumulator (fma.rn.f32x2: two IEEE FMAs per
-// instruction, the same two FMAs per component in the same order as the scalar code), the resident operand sits in
-// shared memory as (b.x, b.y, -b.y, b.x) so that one 16-byte broadcast load feeds both packed FMAs of XT rows, and
-// the streamed operand is read exactly once, KC values of k at a time.
-__device__ __forceinline__ unsigned long long SPack2(float lo, float hi)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float2 SUnpack2(unsigned long long v)
-{
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-
-template <int KC, int Y, int XT>
-__global__ void __launch_bounds__(kStreamThreads, 2)
-    StreamPackedKernel(const float2 *__restrict__ S, const float2 *__restrict__ Rsd, float2 *__restrict__ out,
-                       const __grid_constant__ StreamParams p, const long long stride_s, const long long stride_r,
-                       const long long stride_o)
-{
-    S = reinterpret_cast<const float2 *>(reinterpret_cast<const unsigned char *>(S) + blockIdx.y * stride_s);
-    Rsd = reinterpret_cast<const float2 *>(reinterpret_cast<const unsigned char *>(Rsd) + blockIdx.y * stride_r);
-    out = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(out) + blockIdx.y * stride_o);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *Rm = reinterpret_cast<float4 *>(smem_raw); // [K][Y] as (b.x, b.y, -b.y, b.x)
-    const int tid = threadIdx.x;
-    const int K = 1 << p.log_k;
-    for (int e = tid; e < K * Y; e += kStreamThreads) {
-        const unsigned k = e / Y, y = e % Y;
-        const float2 b = __ldg(Rsd + (ScatterBits(k, p.rk, p.log_k) | ScatterBits(y, p.ry, p.log_y)));
-        Rm[e] = make_float4(b.x, b.y, -b.y, b.x);
-    }
-    constexpr int kLogKC = (KC == 1) ? 0 : (KC == 2) ? 1 : (KC == 4) ? 2 : 3;
-    unsigned long long koff_lo[KC];
-#pragma unroll
-    for (int kk = 0; kk < KC; kk++) {
-        unsigned long long r = 0;
-#pragma unroll
-        for (int q = 0; (1 << q) < KC; q++)
-            if (kk & (1 << q))
-                r |= 1ull << p.cs[q];
-        koff_lo[kk] = r;
-    }
-    const int n_kchunks = K / KC;
-    __syncthreads();
-
-    const long long tile = static_cast<long long>(kStreamThreads) * XT;
-    for (long long x0 = static_cast<long long>(blockIdx.x) * tile; x0 < p.x_count;
-         x0 += static_cast<long long>(gridDim.x) * tile) {
-        long long x[XT];
-        unsigned long long sbase[XT];
-        bool ok[XT];
-#pragma unroll
-        for (int j = 0; j < XT; j++) {
-            x[j] = x0 + j * kStreamThreads + tid;
-            ok[j] = x[j] < p.x_count;
-            sbase[j] = InsertZeros(static_cast<unsigned long long>(ok[j] ? x[j] : 0), p.cs, p.log_k);
-        }
-        unsigned long long acc[XT][Y];
-#pragma unroll
-        for (int j = 0; j < XT; j++)
-#pragma unroll
-            for (int yy = 0; yy < Y; yy++)
-                acc[j][yy] = 0ull;
-        for (int kc = 0; kc < n_kchunks; kc++) {
-            const unsigned long long khi =
-                ScatterBits(static_cast<unsigned long long>(kc), p.cs + kLogKC, p.log_k - kLogKC);
-            float2 a[XT][KC];
-#pragma unroll
-            for (int j = 0; j < XT; j++)
-#pragma unroll
-                for (int kk = 0; kk < KC; kk++)
-                    a[j][kk] = ok[j] ? __ldg(S + (sbase[j] | khi | koff_lo[kk])) : float2{0.f, 0.f};
-            const float4 *rrow = Rm + (kc * KC) * Y;
-#pragma unroll
-            for (int kk = 0; kk < KC; kk++) {
-                unsigned long long ax[XT], ay[XT];
-#pragma unroll
-                for (int j = 0; j < XT; j++) {
-                    ax[j] = SPack2(a[j][kk].x, a[j][kk].x);
-                    ay[j] = SPack2(a[j][kk].y, a[j][kk].y);
-                }
-#pragma unroll
-                for (int yy = 0; yy < Y; yy++) {
-                    const float4 b = rrow[kk * Y + yy];
-                    const unsigned long long b0 = SPack2(b.x, b.y), b1 = SPack2(b.z, b.w);
-#pragma unroll
-                    for (int j = 0; j < XT; j++) {
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][yy]) : "l"(ax[j]), "l"(b0));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j][yy]) : "l"(ay[j]), "l"(b1));
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < XT; j++) {
-            if (!ok[j])
-                continue;
-            if (p.out_y_shift == 0) {
-                float2 *dst = out + (static_cast<unsigned long long>(x[j]) << p.out_x_shift);
-#pragma unroll
-                for (int yy = 0; yy < Y; yy += 2) {
-                    const float2 v0 = SUnpack2(acc[j][yy]), v1 = SUnpack2(acc[j][yy + 1]);
-                    *reinterpret_cast<float4 *>(dst + yy) = make_float4(v0.x, v0.y, v1.x, v1.y);
-                }
-            }
-            else {
-#pragma unroll
-                for (int yy = 0; yy < Y; yy++)
-                    out[(static_cast<unsigned long long>(yy) << p.out_y_shift) + static_cast<unsigned long long>(x[j])] =
-                        SUnpack2(acc[j][yy]);
-            }
-        }
-    }
-}
-
-template <int KC, int Y, int XT>
-int LaunchStreamPackedT(const StreamParams &p, const void *s, const void *r, void *out, cudaStream_t stream, int batch,
-                        long long ss, long long sr, long long so)
-{
-    const long long tile = static_cast<long long>(kStreamThreads) * XT;
-    const long long tiles = (p.x_count + tile - 1) / tile;
-    const size_t smem = sizeof(float4) << (p.log_k + p.log_y);
-    auto kernel = StreamPackedKernel<KC, Y, XT>;
-    if (smem > 48 * 1024)
-        JB_TRY(EnsureDynamicSmem(reinterpret_cast<const void *>(kernel), smem));
-    const long long resident = static_cast<long long>(NumSMs()) * PersistentBlocksPerSM(kernel, kStreamThreads, smem);
-    const int grid = static_cast<int>(std::min<long long>(tiles, std::max<long long>(1, resident / batch)));
-    kernel<<<dim3(grid, batch), kStreamThreads, smem, stream>>>(static_cast<const float2 *>(s), static_cast<const float2 *>(r),
-                                                                static_cast<float2 *>(out), p, ss, sr, so);
-    JB_CUDA(cudaGetLastError());
-    return 0;
-}
-
-bool StreamPackedEnabled()
-{
-    static const bool enabled = [] {
-        const char *e = getenv("JB_STREAM_NO_PACKED");
-        return !(e && e[0] == '1');
-    }();
-    return enabled;
-}
-
-// returns -1 when the shape is not served by the packed kernel
-int LaunchStreamPacked(const StreamParams &p, const void *s, const void *r, void *out, cudaStream_t stream, int batch,
-                       long long ss, long long sr, long long so)
-{
-    const int k = 1 << p.log_k, y = 1 << p.log_y;
-    if (!StreamPackedEnabled() || k < 4 || y < 4 || y > 32 || k * y < 32)
-        return -1;
-    if (k == 4) {
-        if (y == 8)
-            return LaunchStreamPackedT<4, 8, 2>(p, s, r, out, stream, batch, ss, sr, so);
-        if (y == 16)
-            return LaunchStreamPackedT<4, 16, 2>(p, s, r, out, stream, batch, ss, sr, so);
-        return y == 32 ? LaunchStreamPackedT<4, 32, 1>(p, s, r, out, stream, batch, ss, sr, so) : -1;
-    }
-    if (y == 4)
-        return LaunchStreamPackedT<8, 4, 2>(p, s, r, out, stream, batch, ss, sr, so);
-    if (y == 8)
-        return LaunchStreamPackedT<8, 8, 2>(p, s, r, out, stream, batch, ss, sr, so);
-    if (y == 16)
-        return LaunchStreamPackedT<8, 16, 2>(p, s, r, out, stream, batch, ss, sr, so);
-    return LaunchStreamPackedT<8, 32, 1>(p, s, r, out, stream, batch, ss, sr, so);
-}
-
 template <typename R, int KC, int NR>
 int LaunchStreamT(const StreamParams &p, const void *s, const void *r, void *out,
                   cudaStream_t stream, int batch, long long stride_s, long long stride_r, long long stride_o)
@@ -414,11 +242,6 @@ int LaunchStream(const StreamParams &p, const void *s, const void *r, void *out,
                  cudaStream_t stream, int batch = 1, long long ss = 0, long long sr = 0, long long so = 0)
 {
     JB_REQUIRE(batch >= 1 && batch <= 65535, "contract: batch out of range");
-    if constexpr (sizeof(R) == 4) {
-        const int rc = LaunchStreamPacked(p, s, r, out, stream, batch, ss, sr, so);
-        if (rc >= 0)
-            return rc;
-    }
     const int k = 1 << p.log_k;
     if (k >= 8)
         return LaunchStreamK<R, 8>(p, s, r, out, stream, batch, ss, sr, so);
