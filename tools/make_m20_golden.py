@@ -22,7 +22,7 @@ from oracle import ref  # noqa: E402
 
 DATA = os.path.join(ROOT, "data")
 argv = sys.argv[1:]
-stem, peak_log2, only = "sycamore53_m20", 24, []
+stem, peak_log2, only, plan_only = "sycamore53_m20", 24, [], False
 while argv and argv[0].startswith("--"):
     if argv[0] == "--stem":
         stem, argv = argv[1], argv[2:]
@@ -30,6 +30,8 @@ while argv and argv[0].startswith("--"):
         peak_log2, argv = int(argv[1]), argv[2:]
     elif argv[0] == "--dtypes":
         only, argv = argv[1].split(","), argv[2:]
+    elif argv[0] == "--plan-only":
+        plan_only, argv = True, argv[1:]
     else:
         raise SystemExit("unknown option " + argv[0])
 ids = [int(a) for a in argv] or [0, 1234567]
@@ -50,6 +52,10 @@ for i in extra:
     n_sub *= dims[i]
 js["path"] = [list(p) for p in rep["path"]]
 text = json.dumps(js, separators=(",", ":"))
+# the alternative evaluation order, committed so that tests can recompute a slice the same way on the GPU in complex128
+json.dump({"path": js["path"], "sliced_indices": full, "extra_indices": extra, "sub_slices": n_sub,
+           "log2_peak": rep["log2_peak_per_slice"], "jet_flops_per_sub_slice": rep["jet_flops_per_slice"]},
+          open(os.path.join(DATA, stem + ".subslice.json"), "w"))
 print(f"{stem}: {len(sliced)} sliced indices + {len(extra)} extra {extra} -> {n_sub} sub-slices of peak 2^{rep['log2_peak_per_slice']} "
       f"elements, {rep['jet_flops_per_slice']:.3g} Jet-flops each ({n_sub * rep['jet_flops_per_slice']:.3g} per slice; the workload's "
       f"own path: {meta['jet_flops_per_slice']:.3g})", flush=True)
@@ -65,7 +71,7 @@ def _one(args):
     return complex(r[0]), sec, fl
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not plan_only:
     import multiprocessing as mp
     import time
 
