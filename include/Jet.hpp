@@ -5,7 +5,9 @@
 #include "jet/SlicedContractor.hpp"
 #include "jet/TaskBasedContractor.hpp"
 #include "jet/Tensor.hpp"
+#include "jet/TensorHelpers.hpp"
 #include "jet/TensorNetwork.hpp"
 #include "jet/TensorNetworkIO.hpp"
 #include "jet/Utilities.hpp"
 #include "jet/Version.hpp"
+#include "jet/permute/Permuter.hpp"

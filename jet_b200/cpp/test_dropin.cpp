@@ -571,6 +571,55 @@ template <class T> void TestTaskBasedContractorLowering()
     }
 }
 
+// ---- Permuter<Backend> and TensorHelpers::MultiplyTensorData (reference test/Test_Permuter.cpp, Test_TensorHelpers.cpp) ----
+template <class T> void TestPermuterAndHelpers()
+{
+    { // Test_Permuter.cpp: 2-D and 3-D transposes through both back ends, argument checks with the reference's messages
+        const std::vector<T> in = {T(0, 0), T(1, 0), T(2, 0), T(3, 0), T(4, 0), T(5, 0)};
+        Permuter<DefaultPermuter<>> pd;
+        Permuter<QFlexPermuter<>> pq;
+        const std::vector<T> want = {T(0, 0), T(3, 0), T(1, 0), T(4, 0), T(2, 0), T(5, 0)};
+        CHECK(pd.Transpose(in, {2, 3}, {"a", "b"}, {"b", "a"}) == want);
+        CHECK(pq.Transpose(in, {2, 3}, {"a", "b"}, {"b", "a"}) == want);
+        std::vector<T> out(6);
+        pq.Transpose(in, {2, 3}, out, {"a", "b"}, {"b", "a"});
+        CHECK(out == want);
+        std::vector<T> big(2 * 3 * 4 * 5);
+        for (size_t i = 0; i < big.size(); i++)
+            big[i] = T(static_cast<typename T::value_type>(i), -static_cast<typename T::value_type>(i));
+        const auto r = pd.Transpose(big, {2, 3, 4, 5}, {"a", "b", "c", "d"}, {"d", "b", "a", "c"});
+        bool ok = true;
+        for (size_t a = 0; a < 2; a++)
+            for (size_t b = 0; b < 3; b++)
+                for (size_t c = 0; c < 4; c++)
+                    for (size_t d = 0; d < 5; d++)
+                        ok = ok && r[((d * 3 + b) * 2 + a) * 4 + c] == big[((a * 3 + b) * 4 + c) * 5 + d];
+        CHECK(ok);
+        CHECK_THROWS_WITH(pd.Transpose(in, {2, 3}, {"a", "a"}, {"b", "a"}), "Duplicate existing indices found.");
+        CHECK_THROWS_WITH(pd.Transpose(in, {2, 3}, {"a", "b"}, {"b", "b"}), "Duplicate transpose indices found.");
+        CHECK_THROWS_WITH(pd.Transpose(in, {2, 3}, {"a", "b"}, {"b", "c"}), "New indices are an invalid permutation");
+        CHECK_THROWS_WITH(pd.Transpose(in, {2, 2}, {"a", "b"}, {"b", "a"}), "Tensor shape does not match given input tensor data.");
+        CHECK_THROWS_WITH(pd.Transpose(in, {2, 3}, {"a", "b"}, {"b", "a", "c"}), "Tensor shape does not match number of indices.");
+    }
+    { // TensorHelpers.hpp:131-168: GEMM, GEMV, transposed GEMV and DOTU through the one product
+        const std::vector<T> A = {T(1, 0), T(2, 0), T(3, 0), T(4, 0), T(0, 1), T(1, 1)}; // 2 x 3
+        const std::vector<T> B = {T(1, 0), T(0, 1), T(2, 0), T(1, 0), T(0, 0), T(1, -1)}; // 3 x 2
+        std::vector<T> C(4);
+        TensorHelpers::MultiplyTensorData<T>(A, B, C, {"i"}, {"j"}, 2, 2, 3);
+        CHECK(Near(C[0], T(5, 0), 1e-6) && Near(C[1], T(5, -2), 1e-6) && Near(C[2], T(4, 2), 1e-6) && Near(C[3], T(2, 5), 1e-6));
+        const std::vector<T> v = {T(1, 0), T(0, 1), T(2, 0)};
+        std::vector<T> y(2);
+        TensorHelpers::MultiplyTensorData<T>(A, v, y, {"i"}, {}, 2, 1, 3); // A v
+        CHECK(Near(y[0], T(7, 2), 1e-6) && Near(y[1], T(5, 2), 1e-6));
+        std::vector<T> z(2);
+        TensorHelpers::MultiplyTensorData<T>(v, B, z, {}, {"j"}, 1, 2, 3); // v^T B
+        CHECK(Near(z[0], T(1, 2), 1e-6) && Near(z[1], T(2, 0), 1e-6));
+        std::vector<T> s(1);
+        TensorHelpers::MultiplyTensorData<T>(v, v, s, {}, {}, 1, 1, 3); // unconjugated dot
+        CHECK(Near(s[0], T(4, 0), 1e-6));
+    }
+}
+
 // ---- TensorNetworkSerializer (reference test/Test_TensorNetworkIO.cpp) ------------------------------
 template <class T> void TestIO()
 {
@@ -664,6 +713,8 @@ int main(int argc, char **argv)
         TestTensorNetwork<c64>();
         TestTensorNetwork<c128>();
         TestPathInfo();
+        TestPermuterAndHelpers<c64>();
+        TestPermuterAndHelpers<c128>();
         TestTaskBasedContractor();
         TestTaskBasedContractorLowering<c64>();
         TestTaskBasedContractorLowering<c128>();

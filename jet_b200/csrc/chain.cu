@@ -403,21 +403,18 @@ __device__ __forceinline__ void ChainRegisterStage(unsigned char *__restrict__ t
 // One memory warp sits on each of the four schedulers.  Their per-element address work is one XOR
 // (shared-memory side) and one 64-bit add (global side): the thread-independent halves of both maps
 // are tabulated in shared memory once per CTA.
-// Hand-off: named barriers (bar.arrive by the producer, bar.sync by the consumer) full[b] load ->
-// compute and done[b] compute -> store; store -> load ("buffer b is free again") is a counter in shared
-// memory that the load warps poll.
-// Two shapes of the CTA (template parameters NG = compute groups, NB = tile buffers):
-//   NG 2, NB 3: tiles of up to 2^13 complex64 (64 KB each) — the longest chains;
-//   NG 3, NB 5: tiles of up to 2^12 elements — three tiles in the FMA pipe at once (JB_CHAIN_GROUPS=3).
-// complex128 always runs one group over three buffers.
+// Hand-off: named barriers (bar.arrive by the producer, bar.sync by the consumer): full[b] load -> compute,
+// done[b] compute -> store, free[b] store -> load ("buffer b may be overwritten").
+// Template parameters NG = compute groups, NB = tile buffers: complex64 NG 2, NB 3 (tiles of up to 2^13 elements, 64 KB
+// each); complex128 one group over three buffers.  (NG 3 / NB 5 on 2^12 tiles was measured in round 1 and dropped.)
 constexpr int kChainLoadThreads = 64;
 constexpr int kChainStoreThreads = 64;
 constexpr int kChainMemThreads = kChainLoadThreads + kChainStoreThreads;
 constexpr int kChainMemTabLen = 1 << (kChainMaxTileBits - kChainMemLogLanes);
 static_assert(kChainLoadThreads == (1 << kChainMemLogLanes) && kChainStoreThreads == (1 << kChainMemLogLanes),
               "memory warps: one thread per lane of the tile walk");
-// named barriers: full[b] = 1 + b, done[b] = 1 + NB + b, stage barrier of group g = 1 + 2 NB + g (<= 15 in all);
-// "buffer b is free again" (store -> load) is a counter in shared memory, polled by the load warps
+// named barriers: full[b] = 1 + b, done[b] = 1 + NB + b, stage barrier of group g = 1 + 2 NB + g, free[b] = 1 + 2 NB + NG + b
+// (<= 15 in all)
 
 struct __align__(16) ChainMemEntry {
     unsigned long long g; // byte offset in X_0 / X_k
@@ -478,8 +475,8 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     constexpr int GT = 1 << LOGT;                      // threads of one compute group
     constexpr int CT = NG * GT;                        // all compute threads (NG groups, NB tile buffers)
     constexpr int kChainBuffers = NB;
-    constexpr int kBarFull = 1, kBarDone = 1 + NB, kBarCompute = 1 + 2 * NB;
-    static_assert(kBarCompute + NG <= 16, "named barriers");
+    constexpr int kBarFull = 1, kBarDone = 1 + NB, kBarCompute = 1 + 2 * NB, kBarFree = 1 + 2 * NB + NG;
+    static_assert(kBarFree + NB <= 16, "named barriers");
     constexpr int ML = kChainMemLogLanes;
     // complex64: a store thread owns two X_k-adjacent elements (store-index bit 0) -> 16-byte stores
     constexpr int PAIR = sizeof(C) == 8 ? 1 : 0;
@@ -621,11 +618,10 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
             const unsigned long long t = blockIdx.x + static_cast<unsigned long long>(i) * gridDim.x;
             const unsigned long long base = Deposit(t, p.outer_in, p.log_outer) * sizeof(C);
             if (i >= kChainBuffers) {
-                // buffer b has been written out (i / NB) times by both store warps
-                const int want = 2 * (i / kChainBuffers);
-                while (*reinterpret_cast<volatile int *>(free_cnt + b) < want)
-                    __nanosleep(64);
-                __threadfence_block();
+                // buffer b is free again once both store warps have read tile i - NB out of it (they arrive on
+                // free[b] after their last shared-memory read; a named barrier, so that the hand-off is a
+                // synchronisation the hardware — and racecheck — knows about)
+                BarSync(kBarFree + b, kChainLoadThreads + kChainStoreThreads);
             }
             const unsigned buf_s = tiles_s + static_cast<unsigned>(b) * tile_bytes;
             const unsigned char *src = reinterpret_cast<const unsigned char *>(X0) + (base + g_lane);
@@ -691,11 +687,10 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
                     }
                 }
             }
-            // every global store of this thread has read its shared-memory source; one release per warp
-            __threadfence_block();
-            __syncwarp();
-            if ((lt & 31) == 0)
-                atomicAdd(free_cnt + b, 1);
+            // every global store of this thread has read its shared-memory source: hand the buffer back to the
+            // load warps — unless no later tile of this CTA will use it (nobody would wait on that arrival)
+            if (i + kChainBuffers < n_my)
+                BarArrive(kBarFree + b, kChainLoadThreads + kChainStoreThreads);
         }
     }
 }
@@ -733,16 +728,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// complex64 tiles of up to 2^12 elements fit five buffers: three compute groups (experiment: JB_CHAIN_GROUPS=3)
-bool ChainUseThreeGroups(bool is_c64, int log_tile)
-{
-    static const bool enabled = [] {
-        const char *e = getenv("JB_CHAIN_GROUPS");
-        return e && e[0] == '3';
-    }();
-    return enabled && is_c64 && log_tile <= 12;
-}
-
 template <typename R>
 int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk, int slot,
                  cudaStream_t stream, int batch)
@@ -768,8 +753,7 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
         JB_CUDA(cudaGetLastError());
     }
-    const bool wide = ChainUseThreeGroups(sizeof(C) == 8, p.log_tile);
-    const int buffers = wide ? 5 : 3;
+    const int buffers = 3;
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
     // a batch of slices shares the SMs: each slice gets its share of the persistent CTAs, at least one
@@ -782,10 +766,7 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         return 0;
     };
     if constexpr (sizeof(C) == 8) {
-        if (wide)
-            JB_TRY(launch(ChainKernel<R, 3, 5>, ChainCtaThreads(3)));
-        else
-            JB_TRY(launch(ChainKernel<R, 2, 3>, ChainCtaThreads(2)));
+        JB_TRY(launch(ChainKernel<R, 2, 3>, ChainCtaThreads(2)));
     }
     else {
         JB_TRY(launch(ChainKernel<R, 1, 3>, ChainCtaThreads(1)));
@@ -970,8 +951,7 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     {
         const size_t smem =
             spec.elem_bytes == 8
-                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages,
-                                        ChainUseThreeGroups(true, lay.params.log_tile) ? 5 : 3)
+                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, 3)
                 : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, 3);
         if (smem > 227 * 1024) {
             *why = "shared memory";

@@ -265,7 +265,7 @@ def test_m20_per_step_normwise_vs_reference():
             plan.run(12345, 1)
             plan.sync()
             steps = plan.steps()
-            worst, checked = 0.0, 0
+            worst, checked, via_numpy = 0.0, 0, 0
             for st in steps:
                 ma, mb = plan.node_modes(st.node_a), plan.node_modes(st.node_b)
                 if st.m * st.n * st.k > 2 ** 27 or max(st.m * st.k, st.k * st.n, st.m * st.n) > 2 ** 24 or not ma or not mb:
@@ -273,10 +273,18 @@ def test_m20_per_step_normwise_vs_reference():
                 a = plan.node(st.node_a).reshape(plan.node_shape(st.node_a))
                 b = plan.node(st.node_b).reshape(plan.node_shape(st.node_b))
                 c = plan.node(st.node_c)
-                want = ref.contract(ma, a, mb, b)
+                try:
+                    want = ref.contract(ma, a, mb, b)
+                except RuntimeError:
+                    # the reference itself throws on a few operand shapes (std::length_error inside its permuter);
+                    # those steps are checked against the numpy restatement (pinned to the reference, tests/test_oracle.py)
+                    _, w = jo.contract(([str(i) for i in ma], a), ([str(i) for i in mb], b))
+                    want = np.asarray(w).reshape(-1)
+                    via_numpy += 1
                 err = np.linalg.norm(c - want) / max(np.linalg.norm(want), 1e-300)
                 worst = max(worst, err)
                 checked += 1
                 assert err < tol, (dtype, st.node_c, st.m, st.n, st.k, err)
-            assert checked >= 500
-            print(stem, np.dtype(dtype).name, "steps checked", checked, "worst normwise error", worst)
+            assert checked >= 500 and via_numpy <= checked // 10
+            print(stem, np.dtype(dtype).name, "steps checked", checked, "of them against the numpy restatement", via_numpy,
+                  "worst normwise error", worst)
