@@ -161,6 +161,7 @@ void Network(const char *json, const char *sliced, uint64_t value, int mode, int
 
 } // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char *ref_last_error() { return g_error.c_str(); }
@@ -236,3 +237,4 @@ int ref_slice_index(int dtype, int rank, const int64_t *shape, int axis, int64_t
 }
 
 } // extern "C"
+#pragma GCC visibility pop
