@@ -367,7 +367,7 @@ template <class TensorType> class TaskBasedContractor {
     };
 
     // "idx(value)" -> (idx, value) for a node label that is not an index of the tensor
-    static bool ParseSliced_(const std::string &label, std::string *index, size_t *value)
+    static bool SplitSliced_(const std::string &label, size_t *prefix_len, size_t *value) noexcept
     {
         if (label.size() < 4 || label.back() != ')')
             return false;
@@ -380,8 +380,16 @@ template <class TensorType> class TaskBasedContractor {
                 return false;
             v = v * 10 + static_cast<size_t>(label[i] - '0');
         }
-        *index = label.substr(0, open);
+        *prefix_len = open;
         *value = v;
+        return true;
+    }
+    static bool ParseSliced_(const std::string &label, std::string *index, size_t *value)
+    {
+        size_t n = 0;
+        if (!SplitSliced_(label, &n, value))
+            return false;
+        *index = label.substr(0, n);
         return true;
     }
 
@@ -425,11 +433,10 @@ template <class TensorType> class TaskBasedContractor {
                 continue;
             const auto &tidx = leaf.tensor->GetIndices();
             for (const auto &label : leaf.node_indices) {
-                std::string index;
-                size_t value = 0;
+                size_t prefix = 0, value = 0;
                 if (!label.empty() && label.back() == ')' && std::find(tidx.begin(), tidx.end(), label) == tidx.end() &&
-                    ParseSliced_(label, &index, &value)) {
-                    key.Text(index, index.size());
+                    SplitSliced_(label, &prefix, &value)) {
+                    key.Text(label, prefix);
                     key.Byte(0xFD); // a sliced label: the value is not part of the structure
                 }
                 else {
@@ -540,9 +547,8 @@ template <class TensorType> class TaskBasedContractor {
                 const NetworkRecord &net = networks_[group.members[g]];
                 for (size_t l = 0; l < net.leaves.size(); l++)
                     for (size_t q = 0; q < leaf_slicing[l].label_pos.size(); q++) {
-                        std::string index;
-                        size_t value = 0;
-                        ParseSliced_(net.leaves[l].node_indices[leaf_slicing[l].label_pos[q]], &index, &value);
+                        size_t prefix = 0, value = 0;
+                        SplitSliced_(net.leaves[l].node_indices[leaf_slicing[l].label_pos[q]], &prefix, &value);
                         digits[g][leaf_slicing[l].sliced_ids[q]] = value;
                         dims[leaf_slicing[l].sliced_ids[q]] =
                             std::max<int64_t>(dims[leaf_slicing[l].sliced_ids[q]], static_cast<int64_t>(value) + 1);
