@@ -295,6 +295,8 @@ typedef struct jb_op_info_t {
     int32_t n_stages;   /* fused chain: barrier-separated stages */
     int32_t gemm_kind;  /* ttgt: JB_GEMM_* — the GEMM kernel this unit launches */
     double flops, bytes, step_bytes;
+    int32_t register_steps; /* fused chain: steps executed inside register stages (the rest go through shared memory) */
+    int32_t pad;
 } jb_op_info_t;
 int jb_plan_ops(const jb_plan *plan, jb_op_info_t *ops, int32_t cap, int32_t *count);
 /* Like jb_plan_profile, per launch unit: ms[i] is the mean device time of unit i. */

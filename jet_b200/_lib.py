@@ -113,6 +113,8 @@ class OpInfo(C.Structure):
         ("flops", C.c_double),
         ("bytes", C.c_double),
         ("step_bytes", C.c_double),
+        ("register_steps", C.c_int32),
+        ("pad", C.c_int32),
     ]
 
 

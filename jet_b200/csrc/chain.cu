@@ -979,9 +979,12 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     out->conflict_free = lay.conflict_free;
     out->n_stages = lay.params.n_stages;
     out->launches = 1;
+    out->register_steps = 0;
     for (int sg = 0; sg < lay.params.n_stages; sg++)
-        if (lay.params.stage[sg].kind == 1)
+        if (lay.params.stage[sg].kind == 1) {
             out->launches = 2;
+            out->register_steps += lay.params.stage[sg].count;
+        }
     out->modes_c = cur_m;
     out->extent_c = cur_e;
     out->flops = flops;

@@ -165,6 +165,7 @@ struct ChainOp {
     int conflict_free = 1;
     int n_stages = 0;
     int launches = 1; // chain kernel, plus the matrix gather when a register stage reads the constant bank
+    int register_steps = 0; // steps executed inside register stages
     std::vector<unsigned char> blob; // ChainParams (chain_plan.h)
     std::vector<int32_t> modes_c;
     std::vector<int64_t> extent_c;

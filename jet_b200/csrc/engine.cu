@@ -1368,6 +1368,8 @@ int jb_plan_ops(const jb_plan *p, jb_op_info_t *ops, int32_t cap, int32_t *count
         o.n_stages = op.kernel == 2 ? op.chain.n_stages : 0;
         o.gemm_kind = op.kernel == 1 ? p->steps[op.steps[0]].cp.gemm_kind : 0;
         o.flops = o.bytes = o.step_bytes = 0.0;
+        o.register_steps = op.kernel == 2 ? op.chain.register_steps : 0;
+        o.pad = 0;
         if (op.kernel == 2) {
             o.launches = op.chain.launches;
             o.flops = op.chain.flops;
