@@ -328,9 +328,16 @@ template <class TensorType> class TaskBasedContractor {
         const bool stepwise = mode != nullptr && std::string(mode) == "stepwise";
         // names that must hold a tensor after Contract() besides the results: every contraction output that no
         // deletion task removes
+        std::unordered_set<std::string> final_names;
+        for (const auto &st : storages_)
+            final_names.insert(st.name);
         bool survivors = false;
-        for (const auto &c : contractions_)
-            survivors = survivors || (!deleted_.count(c.name_3) && !IsFinalName_(c.name_3));
+        for (const auto &c : contractions_) {
+            if (!deleted_.count(c.name_3) && !final_names.count(c.name_3)) {
+                survivors = true;
+                break;
+            }
+        }
         if (stepwise || (delete_ && survivors)) {
             // (deletion tasks cover only part of the graph: the leaves some surviving tensors would be
             // re-derived from are gone after Contract(), so everything is produced now)
@@ -345,14 +352,6 @@ template <class TensorType> class TaskBasedContractor {
             for (const auto &name : deleted_)
                 name_to_tensor_map_[name] = nullptr;
         intermediates_pending_ = survivors;
-    }
-
-    bool IsFinalName_(const std::string &name) const
-    {
-        for (const auto &s : storages_)
-            if (s.name == name)
-                return true;
-        return false;
     }
 
     void MaterialiseIntermediates_()
@@ -431,6 +430,16 @@ template <class TensorType> class TaskBasedContractor {
             key.Byte(0xFE);
             if (leaf.tensor == nullptr)
                 continue;
+            // A leaf no sliced index touches is the SAME tensor object in every copy (AddContractionTasks keeps one
+            // tensor per task name): its address stands for labels + indices + shape.  Only the few sliced leaves are
+            // hashed by content, with the slice values blanked.
+            bool annotated = false;
+            for (const auto &label : leaf.node_indices)
+                annotated = annotated || (!label.empty() && label.back() == ')');
+            if (!annotated) {
+                key.Number(reinterpret_cast<uintptr_t>(leaf.tensor));
+                continue;
+            }
             const auto &tidx = leaf.tensor->GetIndices();
             for (const auto &label : leaf.node_indices) {
                 size_t prefix = 0, value = 0;
