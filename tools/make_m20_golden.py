@@ -8,7 +8,7 @@ indices to slice for a small peak (the value of a slice does not depend on the c
 sub-slices go through the reference's own sliced flow (jet_sliced.cpp: SliceIndices copies -> AddContractionTasks
 -> AddReductionTask -> Contract); the reduction result IS the slice amplitude — an identity of the contraction,
 not an approximation.  Run in the container that has /root/reference:
-    python tools/make_m20_golden.py [--stem sycamore53_m20] [--peak-log2 24] [--dtypes complex128] [slice ids ...]
+    python tools/make_m20_golden.py [--stem sycamore53_m20] [--peak-log2 24] [--dtypes complex128] [--sub-count 8] [slice ids ...]
 The complex128 value is the truth the tests compare against (1e-12 for the complex128 engine; the complex64 engine
 is compared with it at the accuracy the conditioning of the sum allows, see tests/test_m20_synth.py)."""
 import json
@@ -22,7 +22,7 @@ from oracle import ref  # noqa: E402
 
 DATA = os.path.join(ROOT, "data")
 argv = sys.argv[1:]
-stem, peak_log2, only, plan_only = "sycamore53_m20", 24, [], False
+stem, peak_log2, only, plan_only, sub_count = "sycamore53_m20", 24, [], False, 0
 while argv and argv[0].startswith("--"):
     if argv[0] == "--stem":
         stem, argv = argv[1], argv[2:]
@@ -32,6 +32,8 @@ while argv and argv[0].startswith("--"):
         only, argv = argv[1].split(","), argv[2:]
     elif argv[0] == "--plan-only":
         plan_only, argv = True, argv[1:]
+    elif argv[0] == "--sub-count":
+        sub_count, argv = int(argv[1]), argv[2:]
     else:
         raise SystemExit("unknown option " + argv[0])
 ids = [int(a) for a in argv] or [0, 1234567]
@@ -78,13 +80,16 @@ if __name__ == "__main__" and not plan_only:
     workers = max(1, min(4, (os.cpu_count() or 2) // 2))
     for v in ids:
         e = gold.setdefault(str(v), {})
-        e["extra_indices"], e["sub_slices"] = extra, n_sub
+        # --sub-count n: the reference evaluates only the first n sub-slices (one sub-slice of peak 2^26 costs minutes of
+        # CPU); tests then compare that PARTIAL sum with the same partial sum on the GPU
+        count = sub_count if sub_count > 0 else n_sub
+        e["extra_indices"], e["sub_slices"], e["sub_first"], e["sub_count"] = extra, n_sub, 0, count
         for dt, key in (("complex64", ""), ("complex128", "_c128")):
             if ("re" + key) in e or (only and dt not in only):
                 continue
             t0 = time.time()
             with mp.Pool(workers) as pool:
-                parts = pool.map(_one, [(dt, v * n_sub + j) for j in range(n_sub)], chunksize=1)
+                parts = pool.map(_one, [(dt, v * n_sub + j) for j in range(count)], chunksize=1)
             total = sum(p[0] for p in parts)  # summed in complex128 (Python complex), sub-slice order
             e["re" + key], e["im" + key] = float(total.real), float(total.imag)
             e["jet_flops_reference"], e["ref_seconds_here" + key] = sum(p[2] for p in parts), time.time() - t0

@@ -3,8 +3,8 @@
 
 For every (target width, seed): jet_b200/cpp/pathopt proposes a path + sliced indices; the engine plans it WITHOUT a GPU
 (JB_PLAN_DRY_RUN) and the launch units are costed with a per-kernel model calibrated on B200 measurements
-(fused chain: max(bytes / 3.2 TB/s, flops / 46 TFLOP/s); stream step: max(bytes / 3.0 TB/s, flops / 25 TFLOP/s); permute +
-GEMM step: max(3 x bytes / 4 TB/s, flops / 150 TFLOP/s); + launch latency).  Ranking = estimated GPU-seconds for the WHOLE
+(fused chain: max(bytes / 3.2 TB/s, flops / 46 TFLOP/s); stream step: max(bytes / 3.0 TB/s, flops / 25 TFLOP/s); final dot
+(DotGatherKernel): bytes / 3.0 TB/s; permute + GEMM step: max(3 x bytes / 4 TB/s, flops / 150 TFLOP/s); + launch latency).  Ranking = estimated GPU-seconds for the WHOLE
 amplitude = ms per slice x number of slices.  One JSON line per candidate is appended to the log
 (profiles/r2_m20_path_candidates.jsonl holds the 54 candidates of round 2; the model predicted 221 ms for the chosen
 slice, 215 were measured).
@@ -34,6 +34,8 @@ def estimate_ms(plan) -> float:
             t += max(u.bytes / 3.2e12, u.flops / 46e12) + 4e-6
         elif u.kernel == 0:
             t += max(u.bytes / 3.0e12, u.flops / 25e12) + 4e-6
+        elif u.gemm_kind == 1:  # DOTU / GEMV corner: DotGatherKernel reads both operands once, in place
+            t += u.bytes / 3.0e12 + 1e-5
         else:
             t += max(3 * u.bytes / 4e12, u.flops / 150e12) + 2e-5
     return t * 1e3
