@@ -393,26 +393,31 @@ template <class TensorType> class TaskBasedContractor {
     }
 
     // the structure of a network with the slice values blanked out: equal keys <=> slices of one network.
-    // Two independent 64-bit FNV-1a hashes over (path, per leaf: node labels with "(value)" blanked, tensor
-    // indices, shape) — built without materialising the text (1024 copies x 400 leaves are hashed in a few ms).
+    // Two independent 64-bit hashes over (path, per leaf: node labels with "(value)" blanked, tensor indices,
+    // shape), mixed a word at a time and built without materialising the text (1024 copies x 400 leaves in ~3 ms).
     struct StructureKey {
         uint64_t a = 14695981039346656037ull, b = 0x9E3779B97F4A7C15ull;
-        void Byte(unsigned char c) noexcept
+        void Word(uint64_t v) noexcept // two independent multiply-xorshift mixers, one step per 64-bit word
         {
-            a = (a ^ c) * 1099511628211ull;
-            b = (b ^ (c + 0x5Bu)) * 0x100000001B3ull + 0x632BE59BD9B4E019ull;
+            a = (a ^ v) * 0x100000001B3ull;
+            a ^= a >> 29;
+            b = (b + v + 0x632BE59BD9B4E019ull) * 0xD6E8FEB86659FD93ull;
+            b ^= b >> 32;
         }
+        void Byte(unsigned char c) noexcept { Word(0xA500u | c); }
         void Text(const std::string &t, size_t n) noexcept
         {
-            for (size_t i = 0; i < n; i++)
-                Byte(static_cast<unsigned char>(t[i]));
-            Byte(0xFF);
+            size_t i = 0;
+            for (; i + 8 <= n; i += 8) {
+                uint64_t w;
+                std::memcpy(&w, t.data() + i, 8);
+                Word(w);
+            }
+            uint64_t tail = 0;
+            std::memcpy(&tail, t.data() + i, n - i);
+            Word(tail ^ (static_cast<uint64_t>(n) << 56) ^ 0xFF00000000000000ull);
         }
-        void Number(uint64_t v) noexcept
-        {
-            for (int i = 0; i < 8; i++)
-                Byte(static_cast<unsigned char>(v >> (8 * i)));
-        }
+        void Number(uint64_t v) noexcept { Word(v); }
         bool operator==(const StructureKey &o) const noexcept { return a == o.a && b == o.b; }
     };
     struct StructureKeyHash {
