@@ -583,7 +583,12 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
         return !(e && e[0] == '1');
     }();
     if (defer_enabled) {
-        constexpr int64_t kDeferMaxElems = 1 << 14;
+        // every tensor of the unsliced subtree stays below this (JB_DEFER_MAX_LOG2 overrides, for experiments)
+        const int64_t kDeferMaxElems = [] {
+            const char *e = getenv("JB_DEFER_MAX_LOG2");
+            const int l = e ? atoi(e) : 14;
+            return int64_t(1) << std::max(0, std::min(l, 30));
+        }();
         struct Sym {
             std::vector<int32_t> modes;
             int64_t elems = 1, max_elems = 1;
