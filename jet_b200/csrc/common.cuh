@@ -118,6 +118,10 @@ struct ContractPlan {
     // (no permuted copies): blob = DotGatherParams (contract.cu)
     bool gather_dot = false;
     std::vector<unsigned char> dot_blob;
+    // ttgt, small output (M, N <= 16) and a moderate K, power-of-two extents: one CTA per contraction reads both operands
+    // in place and is batched over slices (SmallGemmGatherKernel); blob = SmallGemmParams (contract.cu)
+    bool small_gemm = false;
+    std::vector<unsigned char> small_blob;
     // stream kernel parameters (opaque blob, see contract.cu)
     std::vector<unsigned char> stream_blob;
     int launches = 1;

@@ -568,6 +568,99 @@ bool DotGatherEnabled()
     return enabled;
 }
 
+
+// ---- small output, moderate K, operands in their original layouts, batched over slices --------------------------------
+// The per-slice part of a small sliced network ends in contractions like 16 x 16 x 4096: through TTGT that is five
+// launches (two permutations, GEMM, split-K reduce) — and with slice batching five launches PER SLICE of the batch,
+// 84 % of a batched m10 replay.  Here one CTA computes the whole M x N output of one slice (blockIdx.y = slice): K is
+// walked in chunks of 64 that are gathered into shared memory straight from the operands' own layouts, thread (m, n)
+// accumulates its output in double, fixed order.
+constexpr int kSmallGemmKT = 64;
+struct SmallGemmParams {
+    int log_m, log_n, log_k;
+    uint8_t m_a[4], n_b[4];   // address bit in A of m bit q / in B of n bit q (least significant first)
+    uint8_t k_a[24], k_b[24]; // address bit in A / B of k bit q
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+    SmallGemmGatherKernel(const typename Cx<R>::type *__restrict__ A, const typename Cx<R>::type *__restrict__ B,
+                          typename Cx<R>::type *__restrict__ Cout, const __grid_constant__ SmallGemmParams p,
+                          const long long stride_a, const long long stride_b, const long long stride_c)
+{
+    using C = typename Cx<R>::type;
+    A = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(A) + blockIdx.y * stride_a);
+    B = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(B) + blockIdx.y * stride_b);
+    Cout = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(Cout) + blockIdx.y * stride_c);
+    __shared__ C As[kSmallGemmKT][16 + 1];
+    __shared__ C Bs[kSmallGemmKT][16];
+    const int M = 1 << p.log_m, N = 1 << p.log_n;
+    const long long K = 1ll << p.log_k;
+    const int tid = threadIdx.x;
+    // thread = (k sub-split, m, n): with fewer than 256 outputs the spare threads split each chunk's k range
+    const int log_mn = p.log_m + p.log_n;
+    const int mn = tid & ((1 << log_mn) - 1), ks = tid >> log_mn, S = 256 >> log_mn;
+    const int m = mn >> p.log_n, n = mn & (N - 1);
+    double re = 0.0, im = 0.0;
+    for (long long k0 = 0; k0 < K; k0 += kSmallGemmKT) {
+        for (int e = tid; e < kSmallGemmKT * M; e += 256) {
+            const int kk = e >> p.log_m, mm = e & (M - 1);
+            const unsigned long long k = static_cast<unsigned long long>(k0 + kk);
+            As[kk][mm] = __ldg(A + (ScatterBits(k, p.k_a, p.log_k) | ScatterBits(static_cast<unsigned long long>(mm), p.m_a, p.log_m)));
+        }
+        for (int e = tid; e < kSmallGemmKT * N; e += 256) {
+            const int kk = e >> p.log_n, nn = e & (N - 1);
+            const unsigned long long k = static_cast<unsigned long long>(k0 + kk);
+            Bs[kk][nn] = __ldg(B + (ScatterBits(k, p.k_b, p.log_k) | ScatterBits(static_cast<unsigned long long>(nn), p.n_b, p.log_n)));
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = ks; kk < kSmallGemmKT; kk += S) {
+            const C a = As[kk][m], b = Bs[kk][n];
+            const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+            re += ar * br - ai * bi;
+            im += ar * bi + ai * br;
+        }
+        __syncthreads();
+    }
+    // sub-splits summed in a fixed order
+    __shared__ double2 red[256];
+    red[tid] = make_double2(re, im);
+    __syncthreads();
+    if (ks == 0) {
+        for (int s2 = 1; s2 < S; s2++) {
+            re += red[(s2 << log_mn) | mn].x;
+            im += red[(s2 << log_mn) | mn].y;
+        }
+        Cout[m * N + n] = C{static_cast<R>(re), static_cast<R>(im)};
+    }
+}
+
+bool SmallGemmEnabled()
+{
+    static const bool enabled = [] {
+        const char *e = getenv("JB_DISABLE_SMALL_GEMM");
+        return !(e && e[0] == '1');
+    }();
+    return enabled;
+}
+
+int LaunchSmallGemm(int dtype, const SmallGemmParams &p, const void *a, const void *b, void *c, cudaStream_t stream,
+                    const BatchArgs *batch)
+{
+    const int nb = batch ? batch->count : 1;
+    JB_REQUIRE(nb >= 1 && nb <= 65535, "contract: batch out of range");
+    const long long sa = batch ? batch->stride_a : 0, sb = batch ? batch->stride_b : 0, sc = batch ? batch->stride_c : 0;
+    if (dtype == JB_C64)
+        SmallGemmGatherKernel<float><<<dim3(1, nb), 256, 0, stream>>>(static_cast<const float2 *>(a), static_cast<const float2 *>(b),
+                                                                     static_cast<float2 *>(c), p, sa, sb, sc);
+    else
+        SmallGemmGatherKernel<double><<<dim3(1, nb), 256, 0, stream>>>(static_cast<const double2 *>(a), static_cast<const double2 *>(b),
+                                                                      static_cast<double2 *>(c), p, sa, sb, sc);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 bool SmallMnEligible(int64_t m, int64_t n, int64_t k)
 {
     auto ok = [](int64_t v) { return v == 1 || v == 2 || v == 4; };
@@ -1004,6 +1097,53 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
     P.kernel = 1;
     P.perm_a.clear();
     P.perm_b.clear();
+    // small output, moderate K: one CTA per contraction, operands read in place, batched over slices
+    if (pow2 && SmallGemmEnabled() && P.m <= 16 && P.n <= 16 && P.k >= 64 && P.k <= (1 << 14)) {
+        std::vector<int> lo_a(rank_a), lo_b(rank_b);
+        int na = 0, nb = 0;
+        for (int i = rank_a - 1; i >= 0; i--) {
+            lo_a[i] = na;
+            na += Log2(extent_a[i]);
+        }
+        for (int j = rank_b - 1; j >= 0; j--) {
+            lo_b[j] = nb;
+            nb += Log2(extent_b[j]);
+        }
+        SmallGemmParams sp;
+        std::memset(&sp, 0, sizeof(sp));
+        for (auto it = left.rbegin(); it != left.rend(); ++it)
+            for (int bbit = 0; bbit < Log2(extent_a[*it]); bbit++)
+                sp.m_a[sp.log_m++] = static_cast<uint8_t>(lo_a[*it] + bbit);
+        for (auto it = right.rbegin(); it != right.rend(); ++it)
+            for (int bbit = 0; bbit < Log2(extent_b[*it]); bbit++)
+                sp.n_b[sp.log_n++] = static_cast<uint8_t>(lo_b[*it] + bbit);
+        // k bits in A's address order (the gather of A is then as contiguous as its layout allows)
+        struct KBit {
+            int a, b;
+        };
+        std::vector<KBit> kb;
+        for (size_t q = 0; q < common_a.size(); q++)
+            for (int bbit = 0; bbit < Log2(extent_a[common_a[q]]); bbit++)
+                kb.push_back({lo_a[common_a[q]] + bbit, lo_b[common_b[q]] + bbit});
+        std::sort(kb.begin(), kb.end(), [](const KBit &x, const KBit &y) { return x.a < y.a; });
+        if (kb.size() <= 24 && na <= 62 && nb <= 62) {
+            sp.log_k = static_cast<int>(kb.size());
+            for (size_t q = 0; q < kb.size(); q++) {
+                sp.k_a[q] = static_cast<uint8_t>(kb[q].a);
+                sp.k_b[q] = static_cast<uint8_t>(kb[q].b);
+            }
+            P.small_gemm = true;
+            P.small_blob.resize(sizeof(sp));
+            std::memcpy(P.small_blob.data(), &sp, sizeof(sp));
+            P.permute_a = P.permute_b = false;
+            P.gemm_kind = JB_GEMM_SMALL_MN;
+            P.launches = 1;
+            P.ws_gemm_off = 0;
+            P.ws_gemm_bytes = 0;
+            P.ws_bytes = 0;
+            return 0;
+        }
+    }
     // DOTU / GEMV corner with a long K: read both operands once, where they lie (DotGatherKernel)
     if (pow2 && DotGatherEnabled() && SmallMnEligible(P.m, P.n, P.k) && P.k >= (1 << 16)) {
         std::vector<int> lo_a(rank_a), lo_b(rank_b);
@@ -1179,8 +1319,13 @@ int LaunchContract(const ContractPlan &P, const void *a, const void *b, void *c,
             return LaunchStream<float>(sp, s, r, c, stream, nb, ss, sr, so);
         return LaunchStream<double>(sp, s, r, c, stream, nb, ss, sr, so);
     }
+    if (P.small_gemm) {
+        SmallGemmParams sp;
+        std::memcpy(&sp, P.small_blob.data(), sizeof(sp));
+        return LaunchSmallGemm(P.dtype, sp, a, b, c, stream, batch);
+    }
     if (nb > 1) {
-        // TTGT units are not batched: the slices of a batch run one after the other through the one workspace
+        // the other TTGT units are not batched: the slices of a batch run one after the other through the one workspace
         for (int z = 0; z < nb; z++) {
             const unsigned char *az = static_cast<const unsigned char *>(a) + z * batch->stride_a;
             const unsigned char *bz = static_cast<const unsigned char *>(b) + z * batch->stride_b;

@@ -1402,16 +1402,20 @@ int jb_plan_profile_ops(jb_plan *p, int64_t slice, int reps, float *ms, int32_t 
         ms[i] = 0.f;
     // one eager pass leaves every per-slice input in place (lifetimes are respected because the
     // units are replayed in plan order)
+    // JB_PROFILE_BATCH=1: time the launch units as the batched graph runs them (`batch` slices per launch, starting
+    // at `slice`); the default times one slice per launch
+    const char *pb = getenv("JB_PROFILE_BATCH");
+    const int prof_batch = (pb && pb[0] == '1' && slice + p->batch <= p->num_slices) ? p->batch : 1;
     std::vector<cudaEvent_t> ev(p->ops.size() + 1);
     for (auto &e : ev)
         JB_CUDA(cudaEventCreate(&e));
     std::vector<double> total(p->ops.size(), 0.0);
     for (int r = 0; r < reps + 1; r++) {
         SetStateKernel<<<1, 1, 0, p->stream>>>(p->At<DeviceState>(p->state_off), slice, -1, 0);
-        JB_TRY(LaunchSliceViews(p, 1));
+        JB_TRY(LaunchSliceViews(p, prof_batch));
         for (size_t i = 0; i < p->ops.size(); i++) {
             JB_CUDA(cudaEventRecord(ev[i], p->stream));
-            JB_TRY(LaunchOp(p, p->ops[i], 1));
+            JB_TRY(LaunchOp(p, p->ops[i], prof_batch));
         }
         JB_CUDA(cudaEventRecord(ev.back(), p->stream));
         JB_CUDA(cudaStreamSynchronize(p->stream));

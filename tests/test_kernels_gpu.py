@@ -386,6 +386,38 @@ def test_contract_both_operands_large_uses_tensor_cores(ops):
 
 
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_contract_small_output_moderate_k_reads_operands_in_place(ops, dtype):
+    """M, N <= 16 and 64 <= K <= 2^14 (the last per-slice steps of the small sliced networks, e.g. 16 x 16 x 4096):
+    SmallGemmGatherKernel, one CTA per contraction, both operands gathered from their original layouts, double
+    accumulation.  Random index orders, dim-2 and dim-4 axes, against the oracle."""
+    rng = np.random.default_rng(29)
+    for trial, (n_common, fa, fb, with_dim4) in enumerate([(12, 4, 4, False), (6, 0, 3, False), (10, 2, 2, True),
+                                                           (14, 1, 0, False), (8, 4, 0, False), (9, 3, 4, True)]):
+        common = [f"k{i}" for i in range(n_common)]
+        dims = {i: 2 for i in common}
+        if with_dim4:
+            dims[common[0]] = 4
+        ia = common + [f"a{i}" for i in range(fa)]
+        ib = common + [f"b{i}" for i in range(fb)]
+        for i in ia + ib:
+            dims.setdefault(i, 2)
+        ia = [ia[i] for i in rng.permutation(len(ia))]
+        ib = [ib[i] for i in rng.permutation(len(ib))]
+        sa, sb = [dims[i] for i in ia], [dims[i] for i in ib]
+        a = rand_c(rng, int(np.prod(sa)), dtype).reshape(sa)
+        b = rand_c(rng, int(np.prod(sb)), dtype).reshape(sb)
+        labels = {name: k for k, name in enumerate(sorted(dims))}
+        info = ops.contract_info(dtype, sa, [labels[i] for i in ia], sb, [labels[i] for i in ib])
+        assert info.kernel == 1 and info.ws_bytes == 0, (trial, info.kernel, info.ws_bytes)
+        got, modes = ops.contract(a, [labels[i] for i in ia], b, [labels[i] for i in ib])
+        idx, want = jo.contract((ia, a), (ib, b))
+        assert [labels[i] for i in idx] == list(modes)
+        scale = np.sqrt(float(info.k))
+        err = np.abs(np.asarray(got, dtype=np.complex128).reshape(-1) - np.asarray(want, dtype=np.complex128).reshape(-1)).max() / scale
+        assert err < TOL[np.dtype(dtype)], (trial, err)
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 def test_contract_final_dot_reads_operands_in_place(ops, dtype):
     """The last step of a closed network: two large tensors contracted over (almost) all indices, M, N in {1, 2, 4},
     K >= 2^16 (DotGatherKernel: both operands read once in their original layouts, no permuted copies; FP64
