@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace jb {
@@ -572,10 +574,14 @@ bool DotGatherEnabled()
 // ---- small output, moderate K, operands in their original layouts, batched over slices --------------------------------
 // The per-slice part of a small sliced network ends in contractions like 16 x 16 x 4096: through TTGT that is five
 // launches (two permutations, GEMM, split-K reduce) — and with slice batching five launches PER SLICE of the batch,
-// 84 % of a batched m10 replay.  Here one CTA computes the whole M x N output of one slice (blockIdx.y = slice): K is
-// walked in chunks of 64 that are gathered into shared memory straight from the operands' own layouts, thread (m, n)
-// accumulates its output in double, fixed order.
+// 84 % of a batched m10 replay.  Here one thread-block CLUSTER computes the whole M x N output of one slice
+// (blockIdx.y = slice).  K is cut into chunks of 64, dealt round-robin to the CTAs of the cluster; a chunk is gathered
+// into shared memory straight from the operands' own layouts (per-thread address offsets precomputed, the next chunk
+// in flight in registers while the current one is multiplied); thread (k sub-split, m, n) sums its products of a chunk
+// in the operand precision and adds the chunk to a double accumulator; sub-splits, then CTAs (through distributed
+// shared memory, in rank order) are added in double.  No workspace, fixed order.
 constexpr int kSmallGemmKT = 64;
+constexpr int kSmallGemmMaxCluster = 8;
 struct SmallGemmParams {
     int log_m, log_n, log_k;
     uint8_t m_a[4], n_b[4];   // address bit in A of m bit q / in B of n bit q (least significant first)
@@ -589,42 +595,71 @@ __global__ void __launch_bounds__(256)
                           const long long stride_a, const long long stride_b, const long long stride_c)
 {
     using C = typename Cx<R>::type;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(cluster.block_rank()), csize = static_cast<int>(cluster.num_blocks());
     A = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(A) + blockIdx.y * stride_a);
     B = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(B) + blockIdx.y * stride_b);
     Cout = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(Cout) + blockIdx.y * stride_c);
     __shared__ C As[kSmallGemmKT][16 + 1];
     __shared__ C Bs[kSmallGemmKT][16];
+    __shared__ double2 red[256];
     const int M = 1 << p.log_m, N = 1 << p.log_n;
-    const long long K = 1ll << p.log_k;
+    const int chunks = 1 << (p.log_k - 6);
     const int tid = threadIdx.x;
     // thread = (k sub-split, m, n): with fewer than 256 outputs the spare threads split each chunk's k range
     const int log_mn = p.log_m + p.log_n;
     const int mn = tid & ((1 << log_mn) - 1), ks = tid >> log_mn, S = 256 >> log_mn;
     const int m = mn >> p.log_n, n = mn & (N - 1);
-    double re = 0.0, im = 0.0;
-    for (long long k0 = 0; k0 < K; k0 += kSmallGemmKT) {
-        for (int e = tid; e < kSmallGemmKT * M; e += 256) {
-            const int kk = e >> p.log_m, mm = e & (M - 1);
-            const unsigned long long k = static_cast<unsigned long long>(k0 + kk);
-            As[kk][mm] = __ldg(A + (ScatterBits(k, p.k_a, p.log_k) | ScatterBits(static_cast<unsigned long long>(mm), p.m_a, p.log_m)));
+    // gather slots of this thread: element e = tid + 256 j of a chunk is (kk, mm) = (e >> log_m, e & (M - 1))
+    unsigned long long off_a[4], off_b[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int e = tid + 256 * j;
+        off_a[j] = ScatterBits(static_cast<unsigned long long>(e >> p.log_m), p.k_a, 6) |
+                   ScatterBits(static_cast<unsigned long long>(e & (M - 1)), p.m_a, p.log_m);
+        off_b[j] = ScatterBits(static_cast<unsigned long long>(e >> p.log_n), p.k_b, 6) |
+                   ScatterBits(static_cast<unsigned long long>(e & (N - 1)), p.n_b, p.log_n);
+    }
+    C ra[4], rb[4];
+    auto fetch = [&](int chunk) {
+        const unsigned long long hi_a = ScatterBits(static_cast<unsigned long long>(chunk), p.k_a + 6, p.log_k - 6);
+        const unsigned long long hi_b = ScatterBits(static_cast<unsigned long long>(chunk), p.k_b + 6, p.log_k - 6);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (tid + 256 * j < kSmallGemmKT * M)
+                ra[j] = __ldg(A + (hi_a | off_a[j]));
+            if (tid + 256 * j < kSmallGemmKT * N)
+                rb[j] = __ldg(B + (hi_b | off_b[j]));
         }
-        for (int e = tid; e < kSmallGemmKT * N; e += 256) {
-            const int kk = e >> p.log_n, nn = e & (N - 1);
-            const unsigned long long k = static_cast<unsigned long long>(k0 + kk);
-            Bs[kk][nn] = __ldg(B + (ScatterBits(k, p.k_b, p.log_k) | ScatterBits(static_cast<unsigned long long>(nn), p.n_b, p.log_n)));
+    };
+    double re = 0.0, im = 0.0;
+    if (rank < chunks)
+        fetch(rank);
+    for (int chunk = rank; chunk < chunks; chunk += csize) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int e = tid + 256 * j;
+            if (e < kSmallGemmKT * M)
+                As[e >> p.log_m][e & (M - 1)] = ra[j];
+            if (e < kSmallGemmKT * N)
+                Bs[e >> p.log_n][e & (N - 1)] = rb[j];
         }
         __syncthreads();
+        if (chunk + csize < chunks)
+            fetch(chunk + csize);
+        R cr = R(0), ci = R(0);
 #pragma unroll 4
         for (int kk = ks; kk < kSmallGemmKT; kk += S) {
             const C a = As[kk][m], b = Bs[kk][n];
-            const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
-            re += ar * br - ai * bi;
-            im += ar * bi + ai * br;
+            cr += a.x * b.x - a.y * b.y;
+            ci += a.x * b.y + a.y * b.x;
         }
+        re += static_cast<double>(cr);
+        im += static_cast<double>(ci);
         __syncthreads();
     }
-    // sub-splits summed in a fixed order
-    __shared__ double2 red[256];
+    // sub-splits of this CTA, then the CTAs of the cluster, each in a fixed order
     red[tid] = make_double2(re, im);
     __syncthreads();
     if (ks == 0) {
@@ -632,8 +667,18 @@ __global__ void __launch_bounds__(256)
             re += red[(s2 << log_mn) | mn].x;
             im += red[(s2 << log_mn) | mn].y;
         }
+        red[mn] = make_double2(re, im);
+    }
+    cluster.sync();
+    if (rank == 0 && ks == 0) {
+        for (int r = 1; r < csize; r++) {
+            const double2 *peer = cluster.map_shared_rank(red, r);
+            re += peer[mn].x;
+            im += peer[mn].y;
+        }
         Cout[m * N + n] = C{static_cast<R>(re), static_cast<R>(im)};
     }
+    cluster.sync(); // peers' shared memory stays alive until rank 0 has read it
 }
 
 bool SmallGemmEnabled()
@@ -645,6 +690,30 @@ bool SmallGemmEnabled()
     return enabled;
 }
 
+template <typename R>
+int LaunchSmallGemmT(const SmallGemmParams &p, const void *a, const void *b, void *c, cudaStream_t stream, int nb, long long sa,
+                     long long sb, long long sc)
+{
+    using C = typename Cx<R>::type;
+    const int chunks = 1 << (p.log_k - 6);
+    const int csize = std::min(kSmallGemmMaxCluster, chunks);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize, nb);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    JB_CUDA(cudaLaunchKernelEx(&cfg, SmallGemmGatherKernel<R>, static_cast<const C *>(a), static_cast<const C *>(b),
+                               static_cast<C *>(c), p, sa, sb, sc));
+    return 0;
+}
+
 int LaunchSmallGemm(int dtype, const SmallGemmParams &p, const void *a, const void *b, void *c, cudaStream_t stream,
                     const BatchArgs *batch)
 {
@@ -652,13 +721,8 @@ int LaunchSmallGemm(int dtype, const SmallGemmParams &p, const void *a, const vo
     JB_REQUIRE(nb >= 1 && nb <= 65535, "contract: batch out of range");
     const long long sa = batch ? batch->stride_a : 0, sb = batch ? batch->stride_b : 0, sc = batch ? batch->stride_c : 0;
     if (dtype == JB_C64)
-        SmallGemmGatherKernel<float><<<dim3(1, nb), 256, 0, stream>>>(static_cast<const float2 *>(a), static_cast<const float2 *>(b),
-                                                                     static_cast<float2 *>(c), p, sa, sb, sc);
-    else
-        SmallGemmGatherKernel<double><<<dim3(1, nb), 256, 0, stream>>>(static_cast<const double2 *>(a), static_cast<const double2 *>(b),
-                                                                      static_cast<double2 *>(c), p, sa, sb, sc);
-    JB_CUDA(cudaGetLastError());
-    return 0;
+        return LaunchSmallGemmT<float>(p, a, b, c, stream, nb, sa, sb, sc);
+    return LaunchSmallGemmT<double>(p, a, b, c, stream, nb, sa, sb, sc);
 }
 
 bool SmallMnEligible(int64_t m, int64_t n, int64_t k)

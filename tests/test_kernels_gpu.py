@@ -387,12 +387,14 @@ def test_contract_both_operands_large_uses_tensor_cores(ops):
 
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 def test_contract_small_output_moderate_k_reads_operands_in_place(ops, dtype):
-    """M, N <= 16 and 64 <= K <= 2^14 (the last per-slice steps of the small sliced networks, e.g. 16 x 16 x 4096):
-    SmallGemmGatherKernel, one CTA per contraction, both operands gathered from their original layouts, double
-    accumulation.  Random index orders, dim-2 and dim-4 axes, against the oracle."""
+    """M, N <= 16 and 64 <= K <= 2^14 (the last per-slice steps of the small sliced networks, e.g. 16 x 16 x 4096), both
+    operands larger than the stream kernel's resident limit.  SmallGemmGatherKernel: one thread-block cluster per contraction, both
+    operands gathered from their original layouts, chunks of 64 products summed in the operand precision and
+    accumulated in double.  Random index orders, dim-2 and dim-4 axes, against the oracle."""
     rng = np.random.default_rng(29)
-    for trial, (n_common, fa, fb, with_dim4) in enumerate([(12, 4, 4, False), (6, 0, 3, False), (10, 2, 2, True),
-                                                           (14, 1, 0, False), (8, 4, 0, False), (9, 3, 4, True)]):
+    for trial, (n_common, fa, fb, with_dim4) in enumerate([(12, 4, 4, False), (13, 0, 3, False), (12, 2, 2, True),
+                                                           (14, 1, 0, False), (13, 4, 0, False), (10, 3, 4, True),
+                                                           (9, 4, 4, False)]):
         common = [f"k{i}" for i in range(n_common)]
         dims = {i: 2 for i in common}
         if with_dim4:
