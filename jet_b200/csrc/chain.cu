@@ -985,6 +985,22 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
             out->launches = 2;
             out->register_steps += lay.params.stage[sg].count;
         }
+    if (const char *dump = getenv("JB_CHAIN_DUMP_STAGES"); dump && dump[0] == '1') {
+        // one line per chain: tile / tensor size and, per stage, kind and the local-bit masks of its steps
+        std::fprintf(stderr, "chain log_x=%d log_tile=%d stages:", static_cast<int>(spec.x0_bits.size()), lay.params.log_tile);
+        for (int sg = 0; sg < lay.params.n_stages; sg++) {
+            const ChainStageParams &G = lay.params.stage[sg];
+            if (G.kind == 1) {
+                std::fprintf(stderr, " R(");
+                for (int t = 0; t < G.count; t++)
+                    std::fprintf(stderr, "%s%u", t ? "," : "", G.desc[t] & 0xffu);
+                std::fprintf(stderr, ")");
+            }
+            else
+                std::fprintf(stderr, " S(k%d,n%d)", lay.params.step[G.first].log_k, lay.params.step[G.first].log_n);
+        }
+        std::fprintf(stderr, "\n");
+    }
     out->modes_c = cur_m;
     out->extent_c = cur_e;
     out->flops = flops;
