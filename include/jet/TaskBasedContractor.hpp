@@ -34,6 +34,7 @@
 #include <future>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <ostream>
 #include <string>
 #include <thread>
@@ -43,10 +44,12 @@
 
 #include "Abort.hpp"
 #include "PathInfo.hpp"
+#include "PlanCache.hpp"
 #include "TensorNetwork.hpp"
 #include "jetb200.h"
 
 namespace Jet {
+
 
 /// Handle of a scheduled task (what tf::Task is to the reference's NameToTaskMap).
 class Task {
@@ -495,9 +498,21 @@ template <class TensorType> class TaskBasedContractor {
         return devices.empty() ? std::vector<int>{0} : devices;
     }
 
+    /// Owns a plan set for the duration of one group: back to the cache when the group succeeded, destroyed otherwise.
     struct MultiGuard {
         jb_multi *m = nullptr;
-        ~MultiGuard() { jb_multi_destroy(m); }
+        std::string key;
+        size_t bytes = 0;
+        bool reusable = false;
+        ~MultiGuard()
+        {
+            if (m == nullptr)
+                return;
+            if (reusable)
+                detail::PlanCache::Get().CheckIn(std::move(key), m, bytes);
+            else
+                jb_multi_destroy(m);
+        }
     };
 
     void RunPlans_()
@@ -652,11 +667,44 @@ template <class TensorType> class TaskBasedContractor {
             d.flags = JB_PLAN_STORE_RESULTS;
             MultiGuard guard;
             const int nd = static_cast<int>(std::min<size_t>(devices.size(), group.members.size()));
-            JET_JB_CHECK(jb_multi_create(&d, nd, devices.data(),
-                                         static_cast<int>(std::min<size_t>(lanes, group.members.size())), &guard.m));
+            const int use_lanes = static_cast<int>(std::min<size_t>(lanes, group.members.size()));
+            // everything the plans depend on except the leaf data
+            {
+                auto put = [&](const void *ptr, size_t bytes) {
+                    guard.key.append(static_cast<const char *>(ptr), bytes);
+                    guard.key.push_back('|');
+                };
+                const int32_t head[4] = {dtype, nd, use_lanes, static_cast<int32_t>(d.flags)};
+                put(head, sizeof(head));
+                put(devices.data(), sizeof(int) * static_cast<size_t>(nd));
+                put(rank.data(), sizeof(int32_t) * rank.size());
+                put(extent.data(), sizeof(int64_t) * extent.size());
+                put(mode.data(), sizeof(int32_t) * mode.size());
+                put(flat_path.data(), sizeof(int32_t) * flat_path.size());
+                put(sliced_modes.data(), sizeof(int32_t) * sliced_modes.size());
+            }
+            guard.m = detail::PlanCache::Get().CheckOut(guard.key);
+            if (guard.m != nullptr) {
+                // same structure as an earlier Contract(): new leaves into the existing plans
+                JET_JB_CHECK(jb_multi_upload(guard.m, data.data()));
+                JET_JB_CHECK(jb_multi_sync(guard.m)); // the host buffers in `rebuilt` are released below
+                JET_JB_CHECK(jb_multi_reset(guard.m));
+            }
+            else if (jb_multi_create(&d, nd, devices.data(), use_lanes, &guard.m) != 0) {
+                // idle cached plan sets hold device memory and constant-bank slots: give them back and try once more
+                guard.m = nullptr;
+                if (!detail::PlanCache::Get().Flush())
+                    JET_ABORT(jb_last_error());
+                JET_JB_CHECK(jb_multi_create(&d, nd, devices.data(), use_lanes, &guard.m));
+            }
             rebuilt.clear(); // uploaded
             jb_plan_stats_t stats;
             JET_JB_CHECK(jb_multi_stats(guard.m, &stats));
+            {
+                int plan_devices = 1, plan_lanes = 1;
+                JET_JB_CHECK(jb_multi_num_plans(guard.m, &plan_devices, &plan_lanes));
+                guard.bytes = stats.arena_bytes * static_cast<size_t>(plan_devices) * static_cast<size_t>(plan_lanes);
+            }
             // a network added twice is one slice id: it runs once and its result is handed to every copy
             std::vector<int64_t> run_ids;
             std::vector<size_t> ordinal_of(group.members.size());
@@ -691,8 +739,10 @@ template <class TensorType> class TaskBasedContractor {
                 all_reduced = all_reduced && rid < reduce_count_;
                 none_reduced = none_reduced && !(reduced_ && rid < reduce_count_);
             }
-            if (none_reduced)
+            if (none_reduced) {
+                guard.reusable = true;
                 continue;
+            }
             // ---- this group's share of the reduction: the device's FP64 sum when every member takes part --------
             std::vector<double> part(2 * elems, 0.0);
             if (all_reduced) {
@@ -708,6 +758,7 @@ template <class TensorType> class TaskBasedContractor {
                     }
                 }
             }
+            guard.reusable = true; // every call into the plan set succeeded
             if (total.empty()) {
                 total = std::move(part);
                 total_indices = indices;

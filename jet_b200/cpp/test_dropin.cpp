@@ -541,6 +541,43 @@ template <class T> void TestTaskBasedContractorLowering()
             alive += ptr != nullptr;
         CHECK(alive == 6); // only the six results survive the deletion tasks
     }
+    { // the same structure again with NEW leaf data: the second Contract() reuses the cached plan set (upload + run)
+      // and must give the new network's results, not the old one's; a third contractor with the cache disabled agrees
+        TN other;
+        for (size_t id = 0; id < tn.NumTensors(); id++) {
+            const auto &node = tn.GetNodes()[id];
+            other.AddTensor(random_tensor(node.tensor.GetIndices(), node.tensor.GetShape()), {});
+        }
+        tensor_t other_full;
+        {
+            TN copy = other;
+            other_full = copy.Contract(path);
+        }
+        auto run = [&](TN &net) {
+            TaskBasedContractor<tensor_t> tbc;
+            for (size_t v = 0; v < num_slices; v++) {
+                TN slice = net;
+                slice.SliceIndices(sliced, v);
+                tbc.AddContractionTasks(slice, PathInfo(slice, path));
+            }
+            tbc.AddReductionTask();
+            tbc.Contract().get();
+            return tbc.GetReductionResult();
+        };
+        const tensor_t first = run(tn);      // creates (or reuses) the plan set of this structure
+        const tensor_t second = run(other);  // cache hit: new leaves uploaded into the same plans
+        const tensor_t third = run(tn);      // and back
+        CHECK(near_tensor(first, full));
+        CHECK(near_tensor(second, other_full));
+        CHECK(!near_tensor(second, full));
+        CHECK(near_tensor(third, full));
+        bool identical = first.GetData().size() == third.GetData().size();
+        for (size_t i = 0; identical && i < first.GetData().size(); i++)
+            identical = first.GetData()[i] == third.GetData()[i];
+        CHECK(identical); // a reused plan set is deterministic: bit-identical to the first run
+        CHECK(Jet::detail::PlanCache::Get().Flush()); // something was cached; released here
+        CHECK(near_tensor(run(other), other_full));   // rebuilt from scratch after the flush
+    }
     { // two unrelated networks (two groups) whose results carry the same indices in different orders
         TN n1, n2;
         n1.AddTensor(random_tensor({"x", "k"}, {3, 4}), {});
