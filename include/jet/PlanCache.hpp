@@ -23,8 +23,9 @@ namespace detail {
  * cached plans and run.  An entry is checked OUT while a contractor uses it, so two threads never share one;
  * at most `JET_B200_PLAN_CACHE` entries (default 2; 0 disables), least recently used first out, and only plan
  * sets whose arenas total at most `JET_B200_PLAN_CACHE_MIB` (default 4096) — larger ones are cheap to rebuild
- * relative to their run time and would pin device memory.  The cache is never destroyed at exit (the CUDA context
- * may already be gone by then).
+ * relative to their run time and would pin device memory.  Idle entries are dropped whenever a plan set of another
+ * structure is created (`Flush`): they would otherwise keep constant-bank slots and device memory from it.  The cache
+ * is never destroyed at exit (the CUDA context may already be gone by then).
  */
 struct PlanCache {
     struct Entry {

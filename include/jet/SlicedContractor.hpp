@@ -140,13 +140,10 @@ template <class TensorType> class SlicedContractor {
         d.sliced_modes = sliced.data();
         d.flags = flags;
         // jb_multi_create releases whatever it had built when a later plan fails (e.g. out of memory on lane 3)
-        if (jb_multi_create(&d, static_cast<int>(devices.size()), devices.data(), lanes, &multi_) != 0) {
-            // plan sets a TaskBasedContractor left in the cache hold device memory and constant-bank slots
-            multi_ = nullptr;
-            if (!detail::PlanCache::Get().Flush())
-                JET_ABORT(jb_last_error());
-            JET_JB_CHECK(jb_multi_create(&d, static_cast<int>(devices.size()), devices.data(), lanes, &multi_));
-        }
+        // plan sets a TaskBasedContractor left in the cache hold device memory and constant-bank slots (a plan that
+        // finds no free slot runs without fused chains): they go before a new plan set is built
+        detail::PlanCache::Get().Flush();
+        JET_JB_CHECK(jb_multi_create(&d, static_cast<int>(devices.size()), devices.data(), lanes, &multi_));
         JET_JB_CHECK(jb_multi_stats(multi_, &stats_));
         JET_JB_CHECK(jb_multi_num_plans(multi_, &num_devices_, &lanes_));
     }

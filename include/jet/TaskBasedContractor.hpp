@@ -690,11 +690,10 @@ template <class TensorType> class TaskBasedContractor {
                 JET_JB_CHECK(jb_multi_sync(guard.m)); // the host buffers in `rebuilt` are released below
                 JET_JB_CHECK(jb_multi_reset(guard.m));
             }
-            else if (jb_multi_create(&d, nd, devices.data(), use_lanes, &guard.m) != 0) {
-                // idle cached plan sets hold device memory and constant-bank slots: give them back and try once more
-                guard.m = nullptr;
-                if (!detail::PlanCache::Get().Flush())
-                    JET_ABORT(jb_last_error());
+            else {
+                // idle plan sets of OTHER structures hold device memory and constant-bank slots (a plan that finds no
+                // free slot runs without fused chains): they go before a new plan set is built
+                detail::PlanCache::Get().Flush();
                 JET_JB_CHECK(jb_multi_create(&d, nd, devices.data(), use_lanes, &guard.m));
             }
             rebuilt.clear(); // uploaded

@@ -575,7 +575,8 @@ template <class T> void TestTaskBasedContractorLowering()
         for (size_t i = 0; identical && i < first.GetData().size(); i++)
             identical = first.GetData()[i] == third.GetData()[i];
         CHECK(identical); // a reused plan set is deterministic: bit-identical to the first run
-        CHECK(Jet::detail::PlanCache::Get().Flush()); // something was cached; released here
+        // something was cached (unless JET_B200_PLAN_CACHE=0); released here
+        CHECK(Jet::detail::PlanCache::Get().Flush() == (Jet::detail::PlanCache::Get().capacity > 0));
         CHECK(near_tensor(run(other), other_full));   // rebuilt from scratch after the flush
     }
     { // two unrelated networks (two groups) whose results carry the same indices in different orders
@@ -738,8 +739,9 @@ void TestSlicedFile(const std::string &file_name)
     SlicedContractor<tensor_t> sc3(file.tensors, path, sliced, 0, 0, 3);
     const c64 via_lanes = sc3.Contract(0, 4).GetScalar();
     CHECK(std::abs(std::complex<double>(via_lanes) - want) / std::abs(want) < 1e-5);
-    CHECK(std::abs(std::complex<double>(sc3.Contract().GetScalar()) - std::complex<double>(sc.Contract().GetScalar())) <
-          1e-6 * std::abs(std::complex<double>(sc.Contract().GetScalar())));
+    const std::complex<double> full3(sc3.Contract().GetScalar()), full(sc.Contract().GetScalar());
+    std::cout << "m10 all 64 slices: " << sc3.NumLanes() << " lanes " << full3 << ", " << sc.NumLanes() << " lanes " << full << std::endl;
+    CHECK(std::abs(full3 - full) < 1e-6 * std::abs(full));
 }
 
 int main(int argc, char **argv)

@@ -753,7 +753,12 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
         JB_CUDA(cudaGetLastError());
     }
-    const int buffers = 3;
+    // tile buffers: 3; JB_CHAIN_BUFFERS=4 (experiments) takes a fourth when the tiles are small enough to fit
+    static const int want_buffers = [] {
+        const char *e = getenv("JB_CHAIN_BUFFERS");
+        return e ? atoi(e) : 3;
+    }();
+    const int buffers = (want_buffers == 4 && ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, 4) <= 227 * 1024) ? 4 : 3;
     const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
     // a batch of slices shares the SMs: each slice gets its share of the persistent CTAs, at least one
@@ -766,10 +771,16 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         return 0;
     };
     if constexpr (sizeof(C) == 8) {
-        JB_TRY(launch(ChainKernel<R, 2, 3>, ChainCtaThreads(2)));
+        if (buffers == 4)
+            JB_TRY(launch(ChainKernel<R, 2, 4>, ChainCtaThreads(2)));
+        else
+            JB_TRY(launch(ChainKernel<R, 2, 3>, ChainCtaThreads(2)));
     }
     else {
-        JB_TRY(launch(ChainKernel<R, 1, 3>, ChainCtaThreads(1)));
+        if (buffers == 4)
+            JB_TRY(launch(ChainKernel<R, 1, 4>, ChainCtaThreads(1)));
+        else
+            JB_TRY(launch(ChainKernel<R, 1, 3>, ChainCtaThreads(1)));
     }
     JB_CUDA(cudaGetLastError());
     return 0;

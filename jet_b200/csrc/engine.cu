@@ -254,7 +254,7 @@ struct jb_plan {
     size_t arena_bytes = 0;
     size_t ws_off = 0, ws_bytes = 0;
     size_t acc_off = 0, store_off = 0, state_off = 0, list_off = 0, descs_off = 0;
-    int chain_slot = -1; // constant-bank slot of the fused chains (-1: none, fusion off)
+    int chain_slot = -1; // constant-bank slot of the chains' register stages (-1: none, chains keep their matrices in shared memory)
     // slice batching: the per-slice tensors (views, per-slice intermediates) live in a region of slice_bytes that
     // is replicated `batch` times from slice_base on; one graph replay then contracts `batch` slices
     int batch = 1;
@@ -315,7 +315,9 @@ int LaunchOp(jb_plan *p, const Op &op, int batch)
             r[i] = NodePtr(p, op.r_nodes[i]);
             ba.stride_r[i] = NodeStride(p, op.r_nodes[i]);
         }
-        return LaunchChain(op.chain, NodePtr(p, op.x0), r, dst, p->chain_slot, p->stream, batch > 1 ? &ba : nullptr);
+        // (a plan without a slot has no register stage: the slot argument is then unused)
+        return LaunchChain(op.chain, NodePtr(p, op.x0), r, dst, p->chain_slot >= 0 ? p->chain_slot : ChainOperatorSlot(),
+                           p->stream, batch > 1 ? &ba : nullptr);
     }
     const Step &st = p->steps[op.steps[0]];
     BatchArgs ba;
@@ -794,11 +796,12 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
     // ---- per-slice launch units: fuse runs of "large tensor absorbs a small tensor" steps ----------
     {
         bool fuse = !keep && !(d->flags & JB_PLAN_NO_FUSE) && ChainFusionEnabled();
-        if (fuse) {
-            // the chains' step matrices go through a constant-bank slot owned by the plan
+        // the matrices of the chains' register stages go through a constant-bank slot owned by the plan; when every
+        // slot of the device is taken (more than five live plans) the chains are still fused, with all their matrices in
+        // shared memory
+        if (fuse)
             p->chain_slot = ChainAcquireSlot(p->device);
-            fuse = p->chain_slot >= 0;
-        }
+        const bool have_slot = p->chain_slot >= 0;
         std::vector<int> consumer(p->nodes.size(), -1);
         for (size_t s = 0; s < p->steps.size(); s++) {
             consumer[p->steps[s].a] = static_cast<int>(s);
@@ -862,7 +865,7 @@ int jb_plan_create(const jb_network_desc_t *d, jb_plan **out)
                 const bool dep_now = r_dep || p->nodes[r_node].slice_dep;
                 ChainOp trial;
                 if (MakeChainOp(p->dtype, p->nodes[x0].modes, p->nodes[x0].extent, operands, max_tile,
-                                &trial, nullptr, !(batch_candidate && dep_now)) != 0) {
+                                &trial, nullptr, have_slot && !(batch_candidate && dep_now)) != 0) {
                     operands.pop_back();
                     break;
                 }

@@ -190,6 +190,29 @@ def test_lane_plans_match_single_plan(data_dir):
         assert b2 == b  # deterministic for a fixed lane count
 
 
+def test_plans_beyond_the_constant_bank_slots_stay_fused(data_dir):
+    """A device has five constant-bank slots for the matrices of the chains' register stages.  The sixth and later
+    live plans must still fuse their chains (matrices in shared memory, no register stage) and give the same sums
+    within complex64 accuracy — not fall back to one kernel per step."""
+    from jet_b200 import ContractionPlan, NetworkFile
+    net = NetworkFile.load(os.path.join(data_dir, "m10.json"), np.complex64)
+    sliced = ["p7", "s7", "h4", "m1", "m2", "I2"]
+    g = gold()
+    e = g["m10_s6_slice0_complex128"]
+    want = complex(e["re"], e["im"])
+    plans = [ContractionPlan(net, sliced) for _ in range(7)]
+    try:
+        chains = [int(p.stats.chains) for p in plans]
+        assert min(chains) > 0 and chains[-1] == chains[0], chains
+        regs = [sum(u.register_steps for u in p.ops()) for p in plans]
+        assert regs[0] >= regs[-1] and regs[-1] == 0, regs  # the last plans found no slot: no register stage
+        for p in (plans[0], plans[-1]):
+            assert rel(p.amplitude([0]).reshape(-1)[0], want) < 1e-5
+    finally:
+        for p in plans:
+            p.close()
+
+
 def test_fully_sliced_leaf_scalar_chain():
     """Regression (found by tools/stress_plan_gpu.py): when every index of a leaf is sliced, the chained
     tensor of a fused run is a scalar and the chain's shared-memory tile holds ONE element; the step matrices

@@ -1,5 +1,5 @@
 """Per-launch-unit profile of one slice of a bench workload (CUDA events on the plan's stream):
-    python tools/plan_profile.py <workload> [slice_id] [--top N]
+    python tools/plan_profile.py <workload> [slice_id] [--top N] [--json FILE]
 Prints plan statistics, the time per unit class (stream / chain / ttgt by GEMM kernel) and the slowest units."""
 import json
 import os
@@ -48,6 +48,17 @@ print("slowest units:")
 for t, i, name, ns, mnk, fl, by in sorted(rows, reverse=True)[:top]:
     print("  #%3d %-22s %8.3f ms steps %2d first (m,n,k)=(2^%.0f,2^%.0f,2^%.0f) %7.1f TFLOP/s %7.1f GB/s" % (
         i, name, t, ns, np.log2(mnk[0]), np.log2(mnk[1]), np.log2(mnk[2]), fl / t / 1e9 if t else 0, by / t / 1e6 if t else 0))
+if "--json" in sys.argv:
+    # every unit with its steps, for offline fits of the kernel cost model (tools/chain_cost_fit.py)
+    dump = []
+    for (t, i, name, ns, mnk, fl, by) in sorted(rows, key=lambda r: r[1]):
+        u = units[i]
+        dump.append(dict(unit=i, name=name, ms=t, flops=fl, bytes=by, log_tile=int(u.log_tile), n_stages=int(u.n_stages),
+                         register_steps=int(u.register_steps),
+                         steps=[[int(steps[q].m), int(steps[q].n), int(steps[q].k)] for q in range(u.first_step, u.last_step + 1)
+                                if steps[q].op == i]))
+    with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+        json.dump(dict(workload=workload, units=dump), f)
 # wall-clock through the graph
 plan.reset(); plan.run(slice_id, 2); plan.sync()
 plan.reset(); t0 = time.time(); plan.run(slice_id, 4); plan.sync(); dt_s = time.time() - t0
