@@ -424,12 +424,17 @@ struct __align__(16) ChainMemEntry {
 
 template <typename R> struct ChainCfg {
     // a compute GROUP works on one tile: 2^kLogThreads threads (== ChainLogThreads in the planner).
-    // complex64 runs two groups on two different tiles, so that one group's FMA phases overlap the
-    // other's shared-memory phases and barriers; complex128 has the registers for one group only.
-    static constexpr int kLogThreads = 8;
+    // complex64 runs FOUR groups of four warps (one warp per scheduler each) on four different tiles: a group
+    // alternates between a shared-memory phase (load 16 elements per thread, store them back, stage barrier) and an
+    // FMA phase; with four independent phase streams per scheduler the FMA pipe rarely finds every warp in a
+    // shared-memory phase (measured with two groups of eight warps: the stage overhead ADDED to the FMA time,
+    // DESIGN §3 K3).  complex128 has the registers for one group of 256 threads only.
+    static constexpr int kLogThreads = sizeof(R) == 4 ? 7 : 8;
     static constexpr int kGroupThreads = 1 << kLogThreads;
+    static constexpr int kGroups = sizeof(R) == 4 ? 4 : 1;
+    static constexpr int kBuffers = sizeof(R) == 4 ? 6 : 3;
 };
-__host__ __device__ constexpr int ChainCtaThreads(int groups) { return groups * 256 + kChainMemThreads; }
+__host__ __device__ constexpr int ChainCtaThreads(int groups, int log_threads) { return (groups << log_threads) + kChainMemThreads; }
 static_assert(ChainCfg<float>::kLogThreads == ChainLogThreads(8) && ChainCfg<double>::kLogThreads == ChainLogThreads(16),
               "planner and kernel must agree on the compute thread count");
 
@@ -445,9 +450,32 @@ __device__ __forceinline__ void BarSync(int id, int count)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-__device__ __forceinline__ void BarArrive(int id, int count)
+// mbarriers (shared-memory address): the tile hand-off between load warps, compute groups and store warps
+__device__ __forceinline__ void MbarInit(unsigned bar, unsigned count)
 {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void MbarArrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrives once every cp.async this thread has issued so far has landed (counts as one of the expected arrivals)
+__device__ __forceinline__ void MbarArriveAfterCpAsync(unsigned bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void MbarWait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "CHAIN_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra CHAIN_DONE;\n\t"
+                 "bra CHAIN_WAIT;\n\t"
+                 "CHAIN_DONE:\n\t"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
 }
 
 template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, int n_stages, int buffers)
@@ -455,7 +483,7 @@ template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, in
     using C = typename Cplx<R>::type;
     const int ct = ChainCfg<R>::kGroupThreads;
     size_t b = sizeof(C) * ((static_cast<size_t>(buffers) * (size_t(1) << log_tile) + 1) & ~size_t(1));
-    b += 64; // free counters
+    b += 256; // mbarriers: full / done / free per tile buffer
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
     b += sizeof(ChainMemEntry) * 2 * kChainMemTabLen;           // load / store tables
     b += sizeof(uint16_t) * static_cast<size_t>(n_stages) * ct; // per-thread stage offsets
@@ -463,7 +491,7 @@ template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, in
 }
 
 template <typename R, int NG, int NB>
-__global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
+__global__ void __launch_bounds__(ChainCtaThreads(NG, ChainCfg<R>::kLogThreads), 1)
     ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
                 typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
                 const __grid_constant__ ChainPtrs rp)
@@ -475,8 +503,8 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     constexpr int GT = 1 << LOGT;                      // threads of one compute group
     constexpr int CT = NG * GT;                        // all compute threads (NG groups, NB tile buffers)
     constexpr int kChainBuffers = NB;
-    constexpr int kBarFull = 1, kBarDone = 1 + NB, kBarCompute = 1 + 2 * NB, kBarFree = 1 + 2 * NB + NG;
-    static_assert(kBarFree + NB <= 16, "named barriers");
+    constexpr int kBarCompute = 1; // named barriers 1 .. NG: the stage barrier of each compute group
+    static_assert(kBarCompute + NG <= 16, "named barriers");
     constexpr int ML = kChainMemLogLanes;
     // complex64: a store thread owns two X_k-adjacent elements (store-index bit 0) -> 16-byte stores
     constexpr int PAIR = sizeof(C) == 8 ? 1 : 0;
@@ -484,8 +512,17 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     C *tiles = reinterpret_cast<C *>(chain_smem);
     const int tile_elems = 1 << p.log_tile;
     // (16-byte aligned also when the tile is a single complex64 element: the matrices are read with float4 loads)
-    int *free_cnt = reinterpret_cast<int *>(tiles + ((kChainBuffers * tile_elems + 1) & ~1)); // [NB], 64 bytes
-    C *Bm = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(free_cnt) + 64);
+    // mbarriers full[NB], done[NB], free[NB] (256 bytes reserved)
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tiles + ((kChainBuffers * tile_elems + 1) & ~1));
+    static_assert(3 * NB * 8 <= 256, "mbarrier area");
+    C *Bm = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(mbar) + 256);
+    const unsigned mbar_s = static_cast<unsigned>(__cvta_generic_to_shared(mbar));
+    // full[b]: the load threads' copies of a tile have landed -> compute group; done[b]: the group has applied the
+    // chain -> store warps; free[b]: the store threads have read the tile out -> load warps.  Tile i lives in
+    // buffer b = i % NB and is the (i / NB)-th use of that buffer's three barriers: waiters pass the phase parity.
+    auto bar_full = [&](int b) { return mbar_s + 8u * static_cast<unsigned>(b); };
+    auto bar_done = [&](int b) { return mbar_s + 8u * static_cast<unsigned>(NB + b); };
+    auto bar_free = [&](int b) { return mbar_s + 8u * static_cast<unsigned>(2 * NB + b); };
     ChainMemEntry *tab_in = reinterpret_cast<ChainMemEntry *>(Bm + ((p.resident_elems + 1) & ~1));
     ChainMemEntry *tab_out = tab_in + kChainMemTabLen;
     uint16_t *atid = reinterpret_cast<uint16_t *>(tab_out + kChainMemTabLen);
@@ -522,8 +559,13 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
         }
     }
 
-    if (tid < 16)
-        free_cnt[tid] = 0;
+    if (tid == 0) {
+        for (int b = 0; b < NB; b++) {
+            MbarInit(bar_full(b), kChainLoadThreads);
+            MbarInit(bar_done(b), GT);
+            MbarInit(bar_free(b), kChainStoreThreads);
+        }
+    }
     // resident operands -> shared memory as K x np matrices (columns n >= N are zero): the matrices
     // of the steps that run through the generic shared-memory path
     for (int s = 0; s < p.n_steps; s++) {
@@ -532,7 +574,7 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
         const int np = q.np;
         const int N = 1 << q.log_n;
         const int total = np << q.log_k;
-        for (int e = tid; e < total; e += ChainCtaThreads(NG)) {
+        for (int e = tid; e < total; e += ChainCtaThreads(NG, LOGT)) {
             const unsigned k = e / np, n = e % np;
             C v = C{R(0), R(0)};
             if (static_cast<int>(n) < N)
@@ -543,8 +585,6 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
     __syncthreads();
 
     const int n_my = static_cast<int>((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x); // tiles of this CTA
-    constexpr int kFullCount = kChainLoadThreads + GT;
-    constexpr int kDoneCount = GT + kChainStoreThreads;
     const unsigned tiles_s = static_cast<unsigned>(__cvta_generic_to_shared(tiles));
     const unsigned tile_bytes = static_cast<unsigned>(tile_elems * sizeof(C));
 
@@ -558,7 +598,8 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
         for (int i = gi; i < n_my; i += NG) {
             const int b = i % kChainBuffers;
             C *tile = tiles + b * tile_elems;
-            BarSync(kBarFull + b, kFullCount);
+            const unsigned use = static_cast<unsigned>(i / kChainBuffers);
+            MbarWait(bar_full(b), use & 1u);
             for (int sg = 0; sg < p.n_stages; sg++) {
                 const ChainStageParams &g = p.stage[sg];
                 const unsigned a_tid = atid[sg * GT + gt];
@@ -590,7 +631,7 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
                 if (sg + 1 < p.n_stages)
                     BarSync(kBarCompute + gi, GT);
             }
-            BarArrive(kBarDone + b, kDoneCount);
+            MbarArrive(bar_done(b)); // release: this thread's tile stores are visible to whoever sees the phase complete
         }
     }
     else if (tid < CT + kChainLoadThreads) {
@@ -619,9 +660,8 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
             const unsigned long long base = Deposit(t, p.outer_in, p.log_outer) * sizeof(C);
             if (i >= kChainBuffers) {
                 // buffer b is free again once both store warps have read tile i - NB out of it (they arrive on
-                // free[b] after their last shared-memory read; a named barrier, so that the hand-off is a
-                // synchronisation the hardware — and racecheck — knows about)
-                BarSync(kBarFree + b, kChainLoadThreads + kChainStoreThreads);
+                // free[b] after their last shared-memory read)
+                MbarWait(bar_free(b), (static_cast<unsigned>(i / kChainBuffers) - 1u) & 1u);
             }
             const unsigned buf_s = tiles_s + static_cast<unsigned>(b) * tile_bytes;
             const unsigned char *src = reinterpret_cast<const unsigned char *>(X0) + (base + g_lane);
@@ -643,9 +683,9 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
                             src + Deposit(jl, p.in_gbit + ML, in_bits) * sizeof(C));
                 }
             }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __threadfence_block();
-            BarArrive(kBarFull + b, kFullCount);
+            // no wait here: the arrival fires when this thread's copies have landed, and the thread moves on to
+            // the next tile (up to NB tiles ahead of the compute groups)
+            MbarArriveAfterCpAsync(bar_full(b));
         }
     }
     else {
@@ -665,7 +705,7 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
             const unsigned long long base = Deposit(t, p.outer_out, p.log_outer) * sizeof(C);
             const unsigned char *buf = reinterpret_cast<const unsigned char *>(tiles) + static_cast<size_t>(b) * tile_bytes;
             unsigned char *dst = reinterpret_cast<unsigned char *>(Xk) + (base + g_lane);
-            BarSync(kBarDone + b, kDoneCount);
+            MbarWait(bar_done(b), static_cast<unsigned>(i / kChainBuffers) & 1u);
             if (ok) {
                 if (pair) {
                     if constexpr (PAIR) {
@@ -690,7 +730,7 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG), 1)
             // every global store of this thread has read its shared-memory source: hand the buffer back to the
             // load warps — unless no later tile of this CTA will use it (nobody would wait on that arrival)
             if (i + kChainBuffers < n_my)
-                BarArrive(kBarFree + b, kChainLoadThreads + kChainStoreThreads);
+                MbarArrive(bar_free(b));
         }
     }
 }
@@ -753,35 +793,18 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
         JB_CUDA(cudaGetLastError());
     }
-    // tile buffers: 3; JB_CHAIN_BUFFERS=4 (experiments) takes a fourth when the tiles are small enough to fit
-    static const int want_buffers = [] {
-        const char *e = getenv("JB_CHAIN_BUFFERS");
-        return e ? atoi(e) : 3;
-    }();
-    const int buffers = (want_buffers == 4 && ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, 4) <= 227 * 1024) ? 4 : 3;
-    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers);
+    constexpr int NG = ChainCfg<R>::kGroups, NB = ChainCfg<R>::kBuffers;
+    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, NB);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
+    JB_REQUIRE(smem <= 227 * 1024, "chain: shared memory");
     // a batch of slices shares the SMs: each slice gets its share of the persistent CTAs, at least one
     const int grid = static_cast<int>(
         std::max<long long>(1, std::min<long long>(p.n_tiles, std::max(1, NumSMs() / batch))));
-    auto launch = [&](auto kernel, int threads) -> int {
-        if (smem > 48 * 1024)
-            JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<dim3(grid, batch), threads, smem, stream>>>(static_cast<const C *>(x0), static_cast<C *>(xk), p, ptrs);
-        return 0;
-    };
-    if constexpr (sizeof(C) == 8) {
-        if (buffers == 4)
-            JB_TRY(launch(ChainKernel<R, 2, 4>, ChainCtaThreads(2)));
-        else
-            JB_TRY(launch(ChainKernel<R, 2, 3>, ChainCtaThreads(2)));
-    }
-    else {
-        if (buffers == 4)
-            JB_TRY(launch(ChainKernel<R, 1, 4>, ChainCtaThreads(1)));
-        else
-            JB_TRY(launch(ChainKernel<R, 1, 3>, ChainCtaThreads(1)));
-    }
+    auto kernel = ChainKernel<R, NG, NB>;
+    if (smem > 48 * 1024)
+        JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<dim3(grid, batch), ChainCtaThreads(NG, ChainCfg<R>::kLogThreads), smem, stream>>>(static_cast<const C *>(x0),
+                                                                                            static_cast<C *>(xk), p, ptrs);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -798,7 +821,7 @@ int ChainMaxTileBits(int dtype)
         const char *e = getenv("JB_CHAIN_TILE_BITS");
         return e ? atoi(e) : 99;
     }();
-    return std::min(cap, dtype == JB_C64 ? 13 : 12);
+    return std::min(cap, 12); // complex64: 6 buffers x 32 KiB; complex128: 3 x 64 KiB
 }
 
 bool ChainFusionEnabled()
@@ -962,8 +985,8 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     {
         const size_t smem =
             spec.elem_bytes == 8
-                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, 3)
-                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, 3);
+                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, ChainCfg<float>::kBuffers)
+                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, ChainCfg<double>::kBuffers);
         if (smem > 227 * 1024) {
             *why = "shared memory";
             return 1;

@@ -33,9 +33,10 @@ constexpr int kChainMaxLogK = 4;
 constexpr int kChainMaxLogN = 4;
 // Threads of one compute group (the threads that share a tile); the kernel may run several groups
 // on different tiles, and the memory warps come on top.
-constexpr int kChainMinLogThreads = 8;
-inline constexpr int ChainLogThreads(int /*elem_bytes*/) { return 8; }
-constexpr int kChainTabLen = 1 << (kChainMaxTileBits - kChainMinLogThreads);
+// complex64: 128 threads (four groups per CTA, tiles of up to 2^12 elements); complex128: 256 (one group).
+inline constexpr int ChainLogThreads(int elem_bytes) { return elem_bytes == 8 ? 7 : 8; }
+// work-index bits above the thread id (j = index >> log_threads): at most 5 (2^12-element tiles on 2^7 threads)
+constexpr int kChainTabLen = 32;
 // The memory warps walk a tile with 2^kChainMemLogLanes lanes (bits above are a per-CTA table).
 constexpr int kChainMemLogLanes = 6;
 
