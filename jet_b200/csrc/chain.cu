@@ -233,6 +233,81 @@ template <> __device__ __forceinline__ double2 ConstB<double>(int idx)
     return make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
 }
 
+// A shared-memory step (complex64) whose matrix comes from the constant bank: the same in-place update as ChainStep,
+// with packed FMAs and the matrix entries as uniform-register operands (no LDS for the matrix, half the FMA issue slots).
+template <int KC, int G, int LOGT>
+__device__ __forceinline__ void ChainStepConst(float2 *__restrict__ tile, const int B, const ChainStepParams &q,
+                                               const uint16_t *__restrict__ gtab, const unsigned a_tid, const int tid)
+{
+    const int log_g = q.log_g;
+    const int log_n = q.log_n;
+    const int N = 1 << log_n;
+    const int np = q.np;
+    unsigned koff[KC];
+#pragma unroll
+    for (int kk = 0; kk < KC; kk++) {
+        unsigned r = 0;
+#pragma unroll
+        for (int b = 0; (1 << b) < KC; b++)
+            if (kk & (1 << b))
+                r ^= q.kcol[b];
+        koff[kk] = r;
+    }
+    unsigned noff_lo[4];
+    noff_lo[0] = 0;
+    noff_lo[1] = log_n >= 1 ? q.ncol[0] : 0u;
+    noff_lo[2] = log_n >= 2 ? q.ncol[1] : 0u;
+    noff_lo[3] = noff_lo[1] ^ noff_lo[2];
+    const unsigned ncol2 = log_n >= 3 ? q.ncol[2] : 0u;
+    const unsigned ncol3 = log_n >= 4 ? q.ncol[3] : 0u;
+    const bool t_ok = tid < (1 << log_g);
+    const int per_thread = log_g > LOGT ? (1 << (log_g - LOGT)) : 1;
+    for (int j0 = 0; j0 < per_thread; j0 += G) {
+        unsigned base[G];
+        bool ok[G];
+        float2 a[G][KC];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int j = j0 + g;
+            ok[g] = t_ok && j < per_thread;
+            base[g] = a_tid ^ gtab[j & 31];
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++)
+                a[g][kk] = ok[g] ? tile[base[g] ^ koff[kk]] : float2{0.f, 0.f};
+        }
+        for (int y0 = 0; y0 < N; y0 += 4) {
+            const unsigned nhi = ((y0 & 4) ? ncol2 : 0u) ^ ((y0 & 8) ? ncol3 : 0u);
+            unsigned long long acc[G][4];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+                    acc[g][yy] = 0ull;
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                float4 r[4];
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+                    r[yy] = ConstB<float>(B + kk * np + y0 + yy);
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        CMulAdd2(acc[g][yy], a[g][kk], r[yy]);
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (!ok[g])
+                    continue;
+#pragma unroll
+                for (int yy = 0; yy < 4; yy++)
+                    if (y0 + yy < N)
+                        tile[base[g] ^ nhi ^ noff_lo[yy]] = Unpack2(acc[g][yy]);
+            }
+        }
+    }
+}
+
 // NL local bits: 4 for complex64 (16 elements = 32 registers), 3 for complex128.
 // B = index of the step's matrix in g_chain_const.
 template <typename R, int NL, int MASK>
@@ -422,21 +497,12 @@ struct __align__(16) ChainMemEntry {
     unsigned pad;
 };
 
-template <typename R> struct ChainCfg {
-    // a compute GROUP works on one tile: 2^kLogThreads threads (== ChainLogThreads in the planner).
-    // complex64 runs FOUR groups of four warps (one warp per scheduler each) on four different tiles: a group
-    // alternates between a shared-memory phase (load 16 elements per thread, store them back, stage barrier) and an
-    // FMA phase; with four independent phase streams per scheduler the FMA pipe rarely finds every warp in a
-    // shared-memory phase (measured with two groups of eight warps: the stage overhead ADDED to the FMA time,
-    // DESIGN §3 K3).  complex128 has the registers for one group of 256 threads only.
-    static constexpr int kLogThreads = sizeof(R) == 4 ? 7 : 8;
-    static constexpr int kGroupThreads = 1 << kLogThreads;
-    static constexpr int kGroups = sizeof(R) == 4 ? 4 : 1;
-    static constexpr int kBuffers = sizeof(R) == 4 ? 6 : 3;
-};
+// A compute GROUP works on one tile: 2^LOGT threads (== ChainLogThreads in the planner).  Kernel shapes:
+//   complex64, default: two groups of 8 warps on two different 2^13-element tiles, three tile buffers;
+//   complex64, JB_CHAIN_LAYOUT=4x128: four groups of 4 warps (one warp per scheduler each) on 2^12-element tiles, six
+//     buffers — more independent phase streams per scheduler, but shorter chains (fewer steps fit a tile);
+//   complex128: one group of 8 warps (register pressure), three buffers of 2^12 elements.
 __host__ __device__ constexpr int ChainCtaThreads(int groups, int log_threads) { return (groups << log_threads) + kChainMemThreads; }
-static_assert(ChainCfg<float>::kLogThreads == ChainLogThreads(8) && ChainCfg<double>::kLogThreads == ChainLogThreads(16),
-              "planner and kernel must agree on the compute thread count");
 
 template <size_t BYTES> __device__ __forceinline__ void CpAsyncElem(unsigned dst, const unsigned char *g)
 {
@@ -478,10 +544,10 @@ __device__ __forceinline__ void MbarWait(unsigned bar, unsigned parity)
                  : "memory");
 }
 
-template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, int n_stages, int buffers)
+template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, int n_stages, int buffers, int log_threads)
 {
     using C = typename Cplx<R>::type;
-    const int ct = ChainCfg<R>::kGroupThreads;
+    const int ct = 1 << log_threads;
     size_t b = sizeof(C) * ((static_cast<size_t>(buffers) * (size_t(1) << log_tile) + 1) & ~size_t(1));
     b += 256; // mbarriers: full / done / free per tile buffer
     b += sizeof(C) * static_cast<size_t>((resident_elems + 1) & ~1);
@@ -490,8 +556,8 @@ template <typename R> size_t ChainSmemBytes(int log_tile, int resident_elems, in
     return b;
 }
 
-template <typename R, int NG, int NB>
-__global__ void __launch_bounds__(ChainCtaThreads(NG, ChainCfg<R>::kLogThreads), 1)
+template <typename R, int LOGT, int NG, int NB>
+__global__ void __launch_bounds__(ChainCtaThreads(NG, LOGT), 1)
     ChainKernel(const typename Cplx<R>::type *__restrict__ X0,
                 typename Cplx<R>::type *__restrict__ Xk, const __grid_constant__ ChainParams p,
                 const __grid_constant__ ChainPtrs rp)
@@ -499,7 +565,6 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG, ChainCfg<R>::kLogThreads),
     using C = typename Cplx<R>::type;
     X0 = reinterpret_cast<const C *>(reinterpret_cast<const unsigned char *>(X0) + blockIdx.y * rp.stride_x0);
     Xk = reinterpret_cast<C *>(reinterpret_cast<unsigned char *>(Xk) + blockIdx.y * rp.stride_xk);
-    constexpr int LOGT = ChainCfg<R>::kLogThreads;
     constexpr int GT = 1 << LOGT;                      // threads of one compute group
     constexpr int CT = NG * GT;                        // all compute threads (NG groups, NB tile buffers)
     constexpr int kChainBuffers = NB;
@@ -610,6 +675,22 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG, ChainCfg<R>::kLogThreads),
                 else {
                     const ChainStepParams &q = p.step[g.first];
                     constexpr bool kF = sizeof(R) == 4;
+                    if constexpr (kF) {
+                        if (p.const_steps) {
+                            const int B = p.const_base + q.b_off;
+                            float2 *ft = reinterpret_cast<float2 *>(tile);
+                            switch (q.log_k) {
+                            case 0: ChainStepConst<1, 4, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
+                            case 1: ChainStepConst<2, 4, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
+                            case 2: ChainStepConst<4, 2, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
+                            case 3: ChainStepConst<8, 2, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
+                            default: ChainStepConst<16, 1, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
+                            }
+                            if (sg + 1 < p.n_stages)
+                                BarSync(kBarCompute + gi, GT);
+                            continue;
+                        }
+                    }
                     switch (q.log_k) {
                     case 0:
                         ChainStep<R, 1, kF ? 4 : 2, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
@@ -782,6 +863,14 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     bool uses_const = false;
     for (int sg = 0; sg < p.n_stages; sg++)
         uses_const = uses_const || p.stage[sg].kind == 1;
+    // JB_CHAIN_CONST_STEPS=1: the shared-memory steps of a complex64 chain read their matrices from the constant bank
+    // too (packed FMAs, uniform operands).  Off by default: measured twice (rounds 1 and 2), one LDCU per two FFMA2
+    // costs more issue slots than the LDS + scalar FMA form saves (m=20: 5.35 -> 5.23 slices/s).
+    static const bool const_steps_enabled = [] {
+        const char *e = getenv("JB_CHAIN_CONST_STEPS");
+        return e && e[0] == '1';
+    }();
+    p.const_steps = uses_const && const_steps_enabled ? 1 : 0;
     if (uses_const) {
         // one set of matrices per launch: the slices of a batch must share every small operand
         for (int st = 0; st < p.n_steps; st++)
@@ -793,18 +882,28 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
         ChainGatherKernel<R><<<std::min(p.n_steps, 8), 256, 0, stream>>>(p, ptrs, static_cast<uint4 *>(sym) + p.const_base);
         JB_CUDA(cudaGetLastError());
     }
-    constexpr int NG = ChainCfg<R>::kGroups, NB = ChainCfg<R>::kBuffers;
-    const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, NB);
     JB_REQUIRE(p.log_threads == ChainLogThreads(static_cast<int>(sizeof(C))), "chain: plan / kernel thread-count mismatch");
-    JB_REQUIRE(smem <= 227 * 1024, "chain: shared memory");
     // a batch of slices shares the SMs: each slice gets its share of the persistent CTAs, at least one
     const int grid = static_cast<int>(
         std::max<long long>(1, std::min<long long>(p.n_tiles, std::max(1, NumSMs() / batch))));
-    auto kernel = ChainKernel<R, NG, NB>;
-    if (smem > 48 * 1024)
-        JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel<<<dim3(grid, batch), ChainCtaThreads(NG, ChainCfg<R>::kLogThreads), smem, stream>>>(static_cast<const C *>(x0),
-                                                                                            static_cast<C *>(xk), p, ptrs);
+    auto launch = [&](auto kernel, int log_threads, int groups, int buffers) -> int {
+        const size_t smem = ChainSmemBytes<R>(p.log_tile, p.resident_elems, p.n_stages, buffers, log_threads);
+        JB_REQUIRE(smem <= 227 * 1024, "chain: shared memory");
+        if (smem > 48 * 1024)
+            JB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<dim3(grid, batch), ChainCtaThreads(groups, log_threads), smem, stream>>>(static_cast<const C *>(x0),
+                                                                                        static_cast<C *>(xk), p, ptrs);
+        return 0;
+    };
+    if constexpr (sizeof(C) == 8) {
+        if (p.log_threads == 7)
+            JB_TRY(launch(ChainKernel<R, 7, 4, 6>, 7, 4, 6));
+        else
+            JB_TRY(launch(ChainKernel<R, 8, 2, 3>, 8, 2, 3));
+    }
+    else {
+        JB_TRY(launch(ChainKernel<R, 8, 1, 3>, 8, 1, 3));
+    }
     JB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -821,7 +920,8 @@ int ChainMaxTileBits(int dtype)
         const char *e = getenv("JB_CHAIN_TILE_BITS");
         return e ? atoi(e) : 99;
     }();
-    return std::min(cap, 12); // complex64: 6 buffers x 32 KiB; complex128: 3 x 64 KiB
+    // 64 KiB per tile buffer (three buffers), or 32 KiB with the four-group layout (six buffers)
+    return std::min(cap, dtype == JB_C64 && !ChainFourGroups() ? 13 : 12);
 }
 
 bool ChainFusionEnabled()
@@ -985,8 +1085,9 @@ int MakeChainOp(int dtype, const std::vector<int32_t> &modes_x, const std::vecto
     {
         const size_t smem =
             spec.elem_bytes == 8
-                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, ChainCfg<float>::kBuffers)
-                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, ChainCfg<double>::kBuffers);
+                ? ChainSmemBytes<float>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages,
+                                        ChainFourGroups() ? 6 : 3, ChainLogThreads(8))
+                : ChainSmemBytes<double>(lay.params.log_tile, lay.params.resident_elems, lay.params.n_stages, 3, ChainLogThreads(16));
         if (smem > 227 * 1024) {
             *why = "shared memory";
             return 1;

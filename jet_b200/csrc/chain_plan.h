@@ -21,6 +21,7 @@
 #include <cstring>
 #include <map>
 #include <set>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -33,8 +34,17 @@ constexpr int kChainMaxLogK = 4;
 constexpr int kChainMaxLogN = 4;
 // Threads of one compute group (the threads that share a tile); the kernel may run several groups
 // on different tiles, and the memory warps come on top.
-// complex64: 128 threads (four groups per CTA, tiles of up to 2^12 elements); complex128: 256 (one group).
-inline constexpr int ChainLogThreads(int elem_bytes) { return elem_bytes == 8 ? 7 : 8; }
+// 256 threads; complex64 with JB_CHAIN_LAYOUT=4x128: 128 threads (four groups per CTA on tiles of up to 2^12 elements
+// instead of two groups on 2^13-element tiles; measured both ways).
+inline bool ChainFourGroups()
+{
+    static const bool four = [] {
+        const char *e = std::getenv("JB_CHAIN_LAYOUT");
+        return e != nullptr && e[0] == '4';
+    }();
+    return four;
+}
+inline int ChainLogThreads(int elem_bytes) { return elem_bytes == 8 && ChainFourGroups() ? 7 : 8; }
 // work-index bits above the thread id (j = index >> log_threads): at most 5 (2^12-element tiles on 2^7 threads)
 constexpr int kChainTabLen = 32;
 // The memory warps walk a tile with 2^kChainMemLogLanes lanes (bits above are a per-CTA table).
@@ -76,6 +86,7 @@ struct ChainParams {
     int32_t resident_elems; // total elements of the resident area
     int32_t const_base;     // first entry of this launch's matrices in the constant bank (set at launch)
     int32_t log_threads;    // compute threads per CTA = 2^log_threads (ChainLogThreads)
+    int32_t const_steps;    // the launch's matrices are in the constant bank: shared-memory steps read them there too (set at launch)
     long long n_tiles;
     uint16_t in_scol[kChainMaxTileBits];  // tile address column of load-index bit q
     uint16_t out_scol[kChainMaxTileBits]; // tile address column of store-index bit q
