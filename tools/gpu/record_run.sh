@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/rec_pytest.log 2>&1; tail -4 gpurun_out/rec_pytest.log
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_chain_gpu.py tests/test_plan_gpu.py -m gpu -x -q -k "not m12 and not large" > gpurun_out/rec_memcheck.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/rec_memcheck.log; tail -3 gpurun_out/rec_memcheck.log
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_chain_gpu.py -m gpu -x -q > gpurun_out/rec_racecheck.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/rec_racecheck.log; tail -3 gpurun_out/rec_racecheck.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "final_dot or dot_and_gemv or dmma" > gpurun_out/rec_memcheck_gemm.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/rec_memcheck_gemm.log; tail -3 gpurun_out/rec_memcheck_gemm.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "final_dot or dot_and_gemv or dmma or small_output" > gpurun_out/rec_memcheck_gemm.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/rec_memcheck_gemm.log; tail -3 gpurun_out/rec_memcheck_gemm.log
 # launch list of one bench step (graph off: ncu cannot replay the graph's kernel nodes; probes and other workloads off)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/rec_launches_m20.csv python bench.py --no-graph --lanes 1 --slices-per-step 1 --steps 1 --warmup 1 --no-cpu --no-others --strong-slices 0 > gpurun_out/rec_ncu_bench.log 2>&1
 # full captures: the heaviest per-slice chain launches and the final dot
