@@ -233,81 +233,6 @@ template <> __device__ __forceinline__ double2 ConstB<double>(int idx)
     return make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
 }
 
-// A shared-memory step (complex64) whose matrix comes from the constant bank: the same in-place update as ChainStep,
-// with packed FMAs and the matrix entries as uniform-register operands (no LDS for the matrix, half the FMA issue slots).
-template <int KC, int G, int LOGT>
-__device__ __forceinline__ void ChainStepConst(float2 *__restrict__ tile, const int B, const ChainStepParams &q,
-                                               const uint16_t *__restrict__ gtab, const unsigned a_tid, const int tid)
-{
-    const int log_g = q.log_g;
-    const int log_n = q.log_n;
-    const int N = 1 << log_n;
-    const int np = q.np;
-    unsigned koff[KC];
-#pragma unroll
-    for (int kk = 0; kk < KC; kk++) {
-        unsigned r = 0;
-#pragma unroll
-        for (int b = 0; (1 << b) < KC; b++)
-            if (kk & (1 << b))
-                r ^= q.kcol[b];
-        koff[kk] = r;
-    }
-    unsigned noff_lo[4];
-    noff_lo[0] = 0;
-    noff_lo[1] = log_n >= 1 ? q.ncol[0] : 0u;
-    noff_lo[2] = log_n >= 2 ? q.ncol[1] : 0u;
-    noff_lo[3] = noff_lo[1] ^ noff_lo[2];
-    const unsigned ncol2 = log_n >= 3 ? q.ncol[2] : 0u;
-    const unsigned ncol3 = log_n >= 4 ? q.ncol[3] : 0u;
-    const bool t_ok = tid < (1 << log_g);
-    const int per_thread = log_g > LOGT ? (1 << (log_g - LOGT)) : 1;
-    for (int j0 = 0; j0 < per_thread; j0 += G) {
-        unsigned base[G];
-        bool ok[G];
-        float2 a[G][KC];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int j = j0 + g;
-            ok[g] = t_ok && j < per_thread;
-            base[g] = a_tid ^ gtab[j & 31];
-#pragma unroll
-            for (int kk = 0; kk < KC; kk++)
-                a[g][kk] = ok[g] ? tile[base[g] ^ koff[kk]] : float2{0.f, 0.f};
-        }
-        for (int y0 = 0; y0 < N; y0 += 4) {
-            const unsigned nhi = ((y0 & 4) ? ncol2 : 0u) ^ ((y0 & 8) ? ncol3 : 0u);
-            unsigned long long acc[G][4];
-#pragma unroll
-            for (int g = 0; g < G; g++)
-#pragma unroll
-                for (int yy = 0; yy < 4; yy++)
-                    acc[g][yy] = 0ull;
-#pragma unroll
-            for (int kk = 0; kk < KC; kk++) {
-                float4 r[4];
-#pragma unroll
-                for (int yy = 0; yy < 4; yy++)
-                    r[yy] = ConstB<float>(B + kk * np + y0 + yy);
-#pragma unroll
-                for (int yy = 0; yy < 4; yy++)
-#pragma unroll
-                    for (int g = 0; g < G; g++)
-                        CMulAdd2(acc[g][yy], a[g][kk], r[yy]);
-            }
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (!ok[g])
-                    continue;
-#pragma unroll
-                for (int yy = 0; yy < 4; yy++)
-                    if (y0 + yy < N)
-                        tile[base[g] ^ nhi ^ noff_lo[yy]] = Unpack2(acc[g][yy]);
-            }
-        }
-    }
-}
-
 // NL local bits: 4 for complex64 (16 elements = 32 registers), 3 for complex128.
 // B = index of the step's matrix in g_chain_const.
 template <typename R, int NL, int MASK>
@@ -675,22 +600,6 @@ __global__ void __launch_bounds__(ChainCtaThreads(NG, LOGT), 1)
                 else {
                     const ChainStepParams &q = p.step[g.first];
                     constexpr bool kF = sizeof(R) == 4;
-                    if constexpr (kF) {
-                        if (p.const_steps) {
-                            const int B = p.const_base + q.b_off;
-                            float2 *ft = reinterpret_cast<float2 *>(tile);
-                            switch (q.log_k) {
-                            case 0: ChainStepConst<1, 4, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
-                            case 1: ChainStepConst<2, 4, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
-                            case 2: ChainStepConst<4, 2, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
-                            case 3: ChainStepConst<8, 2, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
-                            default: ChainStepConst<16, 1, LOGT>(ft, B, q, p.stage_tab[sg], a_tid, gt); break;
-                            }
-                            if (sg + 1 < p.n_stages)
-                                BarSync(kBarCompute + gi, GT);
-                            continue;
-                        }
-                    }
                     switch (q.log_k) {
                     case 0:
                         ChainStep<R, 1, kF ? 4 : 2, LOGT>(tile, Bm, q, p.stage_tab[sg], a_tid, gt);
@@ -863,14 +772,6 @@ int LaunchChainT(ChainParams p, const ChainPtrs &ptrs, const void *x0, void *xk,
     bool uses_const = false;
     for (int sg = 0; sg < p.n_stages; sg++)
         uses_const = uses_const || p.stage[sg].kind == 1;
-    // JB_CHAIN_CONST_STEPS=1: the shared-memory steps of a complex64 chain read their matrices from the constant bank
-    // too (packed FMAs, uniform operands).  Off by default: measured twice (rounds 1 and 2), one LDCU per two FFMA2
-    // costs more issue slots than the LDS + scalar FMA form saves (m=20: 5.35 -> 5.23 slices/s).
-    static const bool const_steps_enabled = [] {
-        const char *e = getenv("JB_CHAIN_CONST_STEPS");
-        return e && e[0] == '1';
-    }();
-    p.const_steps = uses_const && const_steps_enabled ? 1 : 0;
     if (uses_const) {
         // one set of matrices per launch: the slices of a batch must share every small operand
         for (int st = 0; st < p.n_steps; st++)

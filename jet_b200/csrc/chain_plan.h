@@ -86,7 +86,6 @@ struct ChainParams {
     int32_t resident_elems; // total elements of the resident area
     int32_t const_base;     // first entry of this launch's matrices in the constant bank (set at launch)
     int32_t log_threads;    // compute threads per CTA = 2^log_threads (ChainLogThreads)
-    int32_t const_steps;    // the launch's matrices are in the constant bank: shared-memory steps read them there too (set at launch)
     long long n_tiles;
     uint16_t in_scol[kChainMaxTileBits];  // tile address column of load-index bit q
     uint16_t out_scol[kChainMaxTileBits]; // tile address column of store-index bit q

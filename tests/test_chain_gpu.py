@@ -135,3 +135,16 @@ def test_m10_fused_equals_unfused_and_reference(data_dir, dt):
             fa = fused.slice_result(o).reshape(-1)[0]
             pa = plain.slice_result(o).reshape(-1)[0]
             assert abs(fa - pa) / abs(pa) < 10 * TOL[dtype], (sid, fa, pa)
+
+
+def test_four_group_layout_in_a_subprocess():
+    """JB_CHAIN_LAYOUT=4x128 (four compute groups of four warps on 2^12-element tiles, six buffers: the measured
+    alternative to the default two groups on 2^13-element tiles) is read once per process: the random-chain parity
+    test above is repeated in a child process with the variable set."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JB_CHAIN_LAYOUT="4x128")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "random_chains or large_exact"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]

@@ -10,7 +10,7 @@ timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytes
 # launch list of one bench step (graph off: ncu cannot replay the graph's kernel nodes; probes and other workloads off)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/rec_launches_m20.csv python bench.py --no-graph --lanes 1 --slices-per-step 1 --steps 1 --warmup 1 --no-cpu --no-others --strong-slices 0 > gpurun_out/rec_ncu_bench.log 2>&1
 # full captures: the heaviest per-slice chain launches and the final dot
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ChainKernel -s 240 -c 12 -o gpurun_out/rec_chain_m20 -f python bench.py --no-graph --lanes 1 --slices-per-step 1 --steps 1 --warmup 0 --no-cpu --no-others --strong-slices 0 > gpurun_out/rec_ncu_chain.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ChainKernel -s 176 -c 30 -o gpurun_out/rec_chain_m20 -f python bench.py --no-graph --lanes 1 --slices-per-step 1 --steps 1 --warmup 0 --no-cpu --no-others --strong-slices 0 > gpurun_out/rec_ncu_chain.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:DotGather -c 1 -o gpurun_out/rec_dot_m20 -f python bench.py --no-graph --lanes 1 --slices-per-step 1 --steps 1 --warmup 0 --no-cpu --no-others --strong-slices 0 > gpurun_out/rec_ncu_dot.log 2>&1
 timeout 1500 python bench.py > gpurun_out/rec_bench_n1.json 2> gpurun_out/rec_bench_n1.err; tail -2 gpurun_out/rec_bench_n1.err
 timeout 900 python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/rec_bench_ref.json 2> gpurun_out/rec_bench_ref.err
