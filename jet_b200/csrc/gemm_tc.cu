@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -471,7 +472,14 @@ bool GemmTcEligible(int dtype, int64_t m, int64_t n, int64_t k)
         return false;
     // ragged M and N are served by TMA boxes smaller than the tile and a masked epilogue; K must be
     // whole 128-byte swizzle atoms
-    if ((2 * k) % kTcBK != 0 || k < 64 || m < 32 || n < 16 || n % 2 != 0)
+    static const int64_t min_k = [] {
+        // the shortest K (complex) the tensor-core kernel takes: 32 = two k-blocks.  Measured on the one TTGT step of an
+        // m=20 slice (M = 2^21, N = 256, K = 32; tools/gpu/tc_short_k.py): 3.01 ms against 4.81 ms on the FMA GemmKernel,
+        // error 7.8e-7 against 1.5e-7 (normwise, vs float64).  JB_TC_MIN_K overrides.
+        const char *e = getenv("JB_TC_MIN_K");
+        return e ? static_cast<int64_t>(atoll(e)) : int64_t(32);
+    }();
+    if ((2 * k) % kTcBK != 0 || k < min_k || m < 32 || n < 16 || n % 2 != 0)
         return false;
     if (m > (1ll << 30) || n > (1ll << 29) || k > (1ll << 29))
         return false;

@@ -227,10 +227,11 @@ def test_add_and_slice(ops):
 # ---------------------------------------------------------------- tensor-core GEMM (tcgen05, 3xTF32)
 def test_gemm_tensor_core_shapes_vs_fp64(ops):
     """Shapes eligible for the tcgen05 3xTF32 kernel (M % 128 == 0, N % 64 == 0, K % 16 == 0,
-    K >= 64): complex64 result within 1e-5 of the complex128 product (normwise and on the largest
-    elements), i.e. the split keeps FP32-class accuracy."""
+    K >= 32, M N K >= 2^24): complex64 result within 1e-5 of the complex128 product (normwise and on the largest
+    elements), i.e. the split keeps FP32-class accuracy.  (1 << 13, 256, 32) and (4096, 128, 48) are the short-K
+    shapes — one and one and a half accumulation chunks — of the kind one m=20 slice has."""
     rng = np.random.default_rng(41)
-    for m, n, k in [(128, 64, 64), (256, 128, 512), (1024, 1024, 1024), (4096, 512, 2048), (128, 4096, 96), (384, 192, 4000 // 16 * 16)]:
+    for m, n, k in [(1 << 13, 256, 32), (4096, 128, 48), (128, 64, 64), (256, 128, 512), (1024, 1024, 1024), (4096, 512, 2048), (128, 4096, 96), (384, 192, 4000 // 16 * 16)]:
         a = rand_c(rng, m * k, np.complex64).reshape(m, k)
         b = rand_c(rng, k * n, np.complex64).reshape(k, n)
         c = ops.gemm(a, b)
@@ -247,7 +248,7 @@ def test_gemm_tensor_core_ragged_and_split_k(ops):
     the m=20 paths).  Integer data makes FP32 exact, so the result must be bit-identical; random data
     must stay within 2e-6 normwise of the complex128 product."""
     rng = np.random.default_rng(45)
-    shapes = [(64, 512, 256), (32, 1024, 256), (2048, 32, 1024), (4096, 16, 512), (192, 96, 128), (320, 40, 96),
+    shapes = [(1 << 12, 128, 32), (64, 512, 256), (32, 1024, 256), (2048, 32, 1024), (4096, 16, 512), (192, 96, 128), (320, 40, 96),
               (512, 1024, 1 << 14), (256, 64, 1 << 15), (128, 128, 8192), (64, 32, 1 << 14)]
     for m, n, k in shapes:
         a = (rng.integers(-2, 3, (m, k)) + 1j * rng.integers(-2, 3, (m, k))).astype(np.complex64)
