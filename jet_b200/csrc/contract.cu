@@ -439,7 +439,7 @@ constexpr int kDotMaxTileBits = 11;
 constexpr int kDotMaxOuterBits = 56;
 struct DotGatherParams {
     int log_tile, log_outer, log_m, log_n;
-    uint8_t tile_a[kDotMaxTileBits], tile_b[kDotMaxTileBits];   // address bit in A / B of tile bit q (A-ascending)
+    uint8_t tile_a[kDotMaxTileBits], tile_b[kDotMaxTileBits];   // address bit in A / B of tile bit q (bits 0..4 = lanes)
     uint8_t outer_a[kDotMaxOuterBits], outer_b[kDotMaxOuterBits]; // ... of outer bit q
     uint8_t m_a[2], n_b[2];                                       // address bit in A of m bit q / in B of n bit q
 };
@@ -1256,6 +1256,33 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
                 tile.push_back(by_b[q]);
         }
         std::sort(tile.begin(), tile.end(), [](const KBit &x, const KBit &y) { return x.a < y.a; });
+        // which tile bits the LANES of a warp walk (tile bits 0..4): the two lowest A bits and the three lowest B bits
+        // that are not among them — a warp's request then touches ~8 sectors of A and ~8 of B, instead of 8
+        // (fully coalesced) of A and up to 32 of B; the remaining bits follow in A's order.  Measured on the last step
+        // of an m=20 slice (tools/gpu/dot_ab.sh), A bits among the lanes 0..5: 6.03 / 5.12 / 4.93 / 5.15 / 5.52 / 5.59 ms.
+        static const int lane_a_bits = [] {
+            const char *e = getenv("JB_DOT_LANE_A_BITS"); // lane bits taken from A's lowest tile bits (5 = A order)
+            return e ? std::max(0, std::min(5, atoi(e))) : 2;
+        }();
+        if (lane_a_bits < 5 && tile.size() > 5) {
+            std::vector<KBit> lanes(tile.begin(), tile.begin() + lane_a_bits), rest;
+            std::vector<KBit> tile_by_b = tile;
+            std::sort(tile_by_b.begin(), tile_by_b.end(), [](const KBit &x, const KBit &y) { return x.b < y.b; });
+            auto among = [](const std::vector<KBit> &v, const KBit &x) {
+                for (const KBit &t : v)
+                    if (t.a == x.a)
+                        return true;
+                return false;
+            };
+            for (const KBit &v : tile_by_b)
+                if (lanes.size() < 5 && !among(lanes, v))
+                    lanes.push_back(v);
+            for (const KBit &v : tile)
+                if (!among(lanes, v))
+                    rest.push_back(v);
+            tile = lanes;
+            tile.insert(tile.end(), rest.begin(), rest.end());
+        }
         std::vector<KBit> outer;
         for (const KBit &v : by_a)
             if (!in_tile(v))
