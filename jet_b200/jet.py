@@ -6,8 +6,9 @@ engine.  Usage::
     tn = jet.TensorNetwork(dtype=np.complex64)
     tbc = jet.TaskBasedContractor(dtype=np.complex64)
 
-As in the reference the default ``dtype`` is complex128.  The circuit / gate / XIR front end of the
-reference package is out of scope.
+As in the reference the default ``dtype`` is complex128.  The gate / state / circuit classes of the reference package
+(python/jet/{gate,state,circuit}.py) are re-exported from ``jet_b200.gate`` / ``state`` / ``circuit``; the XIR
+interpreter (python/jet/interpreter.py) needs the absent ``xir`` package and is not provided.
 """
 from typing import Union
 
@@ -37,12 +38,19 @@ from .bindings import (  # noqa: F401
     version,
 )
 
+from .circuit import *  # noqa: F401,F403,E402
+from .circuit import __all__ as _circuit_all  # noqa: E402
+from .gate import *  # noqa: F401,F403,E402
+from .gate import __all__ as _gate_all  # noqa: E402
+from .state import *  # noqa: F401,F403,E402
+from .state import __all__ as _state_all  # noqa: E402
+
 __all__ = [
     "PathInfo", "PathStepInfo", "add_tensors", "conj", "contract_tensors", "reshape", "slice_index", "transpose",
     "version", "TaskBasedContractorType", "TensorType", "TensorNetworkType", "TensorNetworkFileType",
     "TensorNetworkSerializerType", "TaskBasedContractor", "Tensor", "TensorNetwork", "TensorNetworkFile",
     "TensorNetworkSerializer", "SlicedContractor",
-]
+] + _circuit_all + _gate_all + _state_all
 
 TaskBasedContractorType = Union[TaskBasedContractorC64, TaskBasedContractorC128]
 TensorType = Union[TensorC64, TensorC128]
