@@ -8,7 +8,9 @@ engine.  Usage::
 
 As in the reference the default ``dtype`` is complex128.  The gate / state / circuit classes of the reference package
 (python/jet/{gate,state,circuit}.py) are re-exported from ``jet_b200.gate`` / ``state`` / ``circuit``; the XIR
-interpreter (python/jet/interpreter.py) needs the absent ``xir`` package and is not provided.
+interpreter's XIR parsing (python/jet/interpreter.py) needs the absent ``xir`` package and is not provided; what it
+computes after parsing is (``jet_b200.simulate``: ``compute_amplitude`` / ``compute_probabilities`` /
+``compute_expected_value``).
 """
 from typing import Union
 
@@ -44,13 +46,15 @@ from .gate import *  # noqa: F401,F403,E402
 from .gate import __all__ as _gate_all  # noqa: E402
 from .state import *  # noqa: F401,F403,E402
 from .state import __all__ as _state_all  # noqa: E402
+from .simulate import *  # noqa: F401,F403,E402
+from .simulate import __all__ as _simulate_all  # noqa: E402
 
 __all__ = [
     "PathInfo", "PathStepInfo", "add_tensors", "conj", "contract_tensors", "reshape", "slice_index", "transpose",
     "version", "TaskBasedContractorType", "TensorType", "TensorNetworkType", "TensorNetworkFileType",
     "TensorNetworkSerializerType", "TaskBasedContractor", "Tensor", "TensorNetwork", "TensorNetworkFile",
     "TensorNetworkSerializer", "SlicedContractor",
-] + _circuit_all + _gate_all + _state_all
+] + _circuit_all + _gate_all + _state_all + _simulate_all
 
 TaskBasedContractorType = Union[TaskBasedContractorC64, TaskBasedContractorC128]
 TensorType = Union[TensorC64, TensorC128]

@@ -331,3 +331,50 @@ def test_circuit_through_the_dropin_bindings():
     tbc.add_contraction_tasks(tn, jet.PathInfo(tn, net.path))
     tbc.contract()
     assert complex(tbc.results[0].scalar).real == pytest.approx(-0.8414709848078962)
+
+
+@pytest.mark.gpu
+def test_simulate_helpers_known_answers_and_statevector():
+    """The quantities the reference's interpreter returns (python/tests/test_interpreter.py:309-520, the programs built
+    directly as circuits): amplitudes, probabilities, expected values."""
+    from jet_b200 import simulate as sim
+
+    # X | [0]; amplitude(state: [0]) -> 0, amplitude(state: [1]) -> 1
+    c = jc.Circuit(1)
+    c.append_gate(jg.PauliX(), [0])
+    assert [sim.compute_amplitude(c, [b]) for b in (0, 1)] == pytest.approx([0, 1])
+    assert sim.compute_probabilities(c) == pytest.approx([0, 1])
+    assert sim.compute_probabilities(jc.Circuit(1)) == pytest.approx([1, 0])          # one tensor: nothing to contract
+    assert sim.compute_probabilities(jc.Circuit(3)) == pytest.approx([1] + [0] * 7)
+    # Bell pair
+    c = jc.Circuit(2)
+    c.append_gate(jg.GateFactory.create("H"), [0])
+    c.append_gate(jg.GateFactory.create("CNOT"), [0, 1])
+    amps = [sim.compute_amplitude(c, [a, b]) for a in (0, 1) for b in (0, 1)]
+    assert amps == pytest.approx([R2, 0, 0, R2])
+    assert sim.compute_probabilities(c) == pytest.approx([0.5, 0, 0, 0.5])
+    assert len(list(c.operations)) == 4  # the circuit handed in is untouched
+    # TwoModeSqueezing(3, 1) | [0, 1] at the default dimension 2 (test_interpreter.py:342-355)
+    c = jc.Circuit(2)
+    c.append_gate(jg.TwoModeSqueezing(3, 1), [0, 1])
+    amps = [sim.compute_amplitude(c, [a, b]) for a in (0, 1) for b in (0, 1)]
+    assert amps == pytest.approx([0.0993279274194332, 0, 0, 0.053401711152745175 + 0.08316823745907517j])
+    # expected value (test_circuit.py:155-165)
+    c = jc.Circuit(2)
+    c.append_gate(jg.GateFactory.create("RX", 1), [0])
+    c.append_gate(jg.GateFactory.create("RY", 2), [1])
+    c.append_gate(jg.GateFactory.create("CNOT"), [0, 1])
+    obs = [jc.Operation(part=jg.GateFactory.create("Y"), wire_ids=[0]), jc.Operation(part=jg.GateFactory.create("X"), wire_ids=[1])]
+    assert sim.compute_expected_value(c, obs).real == pytest.approx(-0.8414709848078962)
+    # random 8-qubit circuit: probabilities and <Z_3> against the state vector, complex64 too
+    rc = _random_circuit(np.random.default_rng(31), 8, 4)
+    psi = _statevector(rc)
+    p = sim.compute_probabilities(rc)
+    assert p.real == pytest.approx((np.abs(psi) ** 2).reshape(-1), abs=1e-12) and abs(p.real.sum() - 1) < 1e-12
+    z3 = np.sum(np.abs(psi) ** 2 * np.where(np.arange(2).reshape([1, 1, 1, 2, 1, 1, 1, 1]) == 0, 1.0, -1.0))
+    got = sim.compute_expected_value(rc, [jc.Operation(part=jg.PauliZ(), wire_ids=[3])])
+    assert got.real == pytest.approx(z3, abs=1e-12)
+    got32 = sim.compute_expected_value(rc, [jc.Operation(part=jg.PauliZ(), wire_ids=[3])], dtype=np.complex64)
+    assert got32.real == pytest.approx(z3, abs=1e-5)
+    with pytest.raises(ValueError, match=r"The state has 1 \(!= 8\) entries."):
+        sim.compute_amplitude(rc, [0])
