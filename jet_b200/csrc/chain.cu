@@ -170,6 +170,12 @@ __device__ __forceinline__ void ChainStep(typename Cplx<R>::type *__restrict__ t
 #pragma unroll
                     for (int g = 0; g < G; g++)
                         CMulAdd(acc[g][yy], a[g][kk], r[yy]);
+                // complex128 with K >= 8: without a fence the compiler hoists the matrix loads of all K rows to the top
+                // (K x 4 x 4 registers) and spills (692 bytes of spill stores in the K = 16 step of the GBS chains)
+                if constexpr (sizeof(C) == 16 && KC >= 8) {
+                    if ((kk & 7) == 7)
+                        asm volatile("" ::: "memory");
+                }
             }
 #pragma unroll
             for (int g = 0; g < G; g++) {
