@@ -8,9 +8,9 @@ engine.  Usage::
 
 As in the reference the default ``dtype`` is complex128.  The gate / state / circuit classes of the reference package
 (python/jet/{gate,state,circuit}.py) are re-exported from ``jet_b200.gate`` / ``state`` / ``circuit``; the XIR
-interpreter's XIR parsing (python/jet/interpreter.py) needs the absent ``xir`` package and is not provided; what it
-computes after parsing is (``jet_b200.simulate``: ``compute_amplitude`` / ``compute_probabilities`` /
-``compute_expected_value``).
+interpreter (python/jet/interpreter.py: ``get_xir_manifest``, ``run_xir_program``) runs on programs read by
+``jet_b200.xir_lite.parse_script`` — the ``xir`` package is absent here — and contracts through ``jet_b200.simulate``
+(``compute_amplitude`` / ``compute_probabilities`` / ``compute_expected_value``).
 """
 from typing import Union
 
@@ -48,13 +48,15 @@ from .state import *  # noqa: F401,F403,E402
 from .state import __all__ as _state_all  # noqa: E402
 from .simulate import *  # noqa: F401,F403,E402
 from .simulate import __all__ as _simulate_all  # noqa: E402
+from .interpreter import *  # noqa: F401,F403,E402
+from .interpreter import __all__ as _interpreter_all  # noqa: E402
 
 __all__ = [
     "PathInfo", "PathStepInfo", "add_tensors", "conj", "contract_tensors", "reshape", "slice_index", "transpose",
     "version", "TaskBasedContractorType", "TensorType", "TensorNetworkType", "TensorNetworkFileType",
     "TensorNetworkSerializerType", "TaskBasedContractor", "Tensor", "TensorNetwork", "TensorNetworkFile",
     "TensorNetworkSerializer", "SlicedContractor",
-] + _circuit_all + _gate_all + _state_all + _simulate_all
+] + _circuit_all + _gate_all + _state_all + _simulate_all + _interpreter_all
 
 TaskBasedContractorType = Union[TaskBasedContractorC64, TaskBasedContractorC128]
 TensorType = Union[TensorC64, TensorC128]
