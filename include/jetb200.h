@@ -285,6 +285,8 @@ int jb_plan_profile(jb_plan *plan, int64_t slice, int reps, float *ms, int32_t c
 #define JB_GEMM_SMALL_MN 1 /* SmallMnKernel: DOTU / GEMV corner with a long K */
 #define JB_GEMM_TCGEN05 2  /* GemmTf32x3Kernel: tcgen05 3xTF32 (complex64) */
 #define JB_GEMM_DMMA 3     /* GemmDmmaKernel: FP64 tensor pipe (complex128) */
+#define JB_GEMM_DOT_GATHER 4   /* DotGatherKernel: DOTU / GEMV corner, both operands read in their original layouts */
+#define JB_GEMM_SMALL_GATHER 5 /* SmallGemmGatherKernel: M, N <= 16, moderate K, operands in place, batched over slices */
 typedef struct jb_op_info_t {
     int32_t kernel;     /* 0 stream, 1 ttgt, 2 fused chain */
     int32_t n_steps;    /* path steps executed by this unit */

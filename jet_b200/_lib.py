@@ -118,7 +118,8 @@ class OpInfo(C.Structure):
     ]
 
 
-GEMM_KIND_NAMES = {0: "GemmKernel", 1: "SmallMnKernel", 2: "GemmTf32x3Kernel", 3: "GemmDmmaKernel"}
+GEMM_KIND_NAMES = {0: "GemmKernel", 1: "SmallMnKernel", 2: "GemmTf32x3Kernel", 3: "GemmDmmaKernel", 4: "DotGatherKernel",
+                   5: "SmallGemmGatherKernel"}
 
 
 class ChainDesc(C.Structure):

@@ -1200,7 +1200,7 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
             P.small_blob.resize(sizeof(sp));
             std::memcpy(P.small_blob.data(), &sp, sizeof(sp));
             P.permute_a = P.permute_b = false;
-            P.gemm_kind = JB_GEMM_SMALL_MN;
+            P.gemm_kind = JB_GEMM_SMALL_GATHER;
             P.launches = 1;
             P.ws_gemm_off = 0;
             P.ws_gemm_bytes = 0;
@@ -1302,7 +1302,7 @@ int MakeContractPlan(int dtype, int rank_a, const int64_t *extent_a, const int32
             P.dot_blob.resize(sizeof(dp));
             std::memcpy(P.dot_blob.data(), &dp, sizeof(dp));
             P.permute_a = P.permute_b = false;
-            P.gemm_kind = JB_GEMM_SMALL_MN;
+            P.gemm_kind = JB_GEMM_DOT_GATHER;
             P.launches = 2;
             P.ws_gemm_off = 0;
             P.ws_gemm_bytes = sizeof(double2) * static_cast<size_t>(DotGatherBlocks(dp)) * static_cast<size_t>(P.m * P.n);

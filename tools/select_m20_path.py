@@ -34,7 +34,7 @@ def estimate_ms(plan) -> float:
             t += max(u.bytes / 3.2e12, u.flops / 46e12) + 4e-6
         elif u.kernel == 0:
             t += max(u.bytes / 3.0e12, u.flops / 25e12) + 4e-6
-        elif u.gemm_kind == 1:  # DOTU / GEMV corner: DotGatherKernel reads both operands once, in place
+        elif u.gemm_kind in (1, 4):  # DOTU / GEMV corner: DotGatherKernel reads both operands once, in place
             t += u.bytes / 3.0e12 + 1e-5
         else:
             t += max(3 * u.bytes / 4e12, u.flops / 150e12) + 2e-5
